@@ -1,0 +1,1425 @@
+// libb200env: fused batched step of custom_envs' optimisation environments for sm_100a.
+//
+// One CTA owns one env for the whole step.  Per env-step (MultiOptLRs semantics, reference
+// envs/multioptlrs.py:80-129) the CTA
+//   1. gathers the minibatch rows into shared memory (reference dataset/inmemorydataset.py:24-28),
+//   2. forward/backward at w_{t-1}  ->  g0                     (problems/optimize_nn.py:122-126),
+//   3. w_t = w_{t-1} - g0 * 10^(a-4), streams w_t back to HBM  (multioptlrs.py:86-87),
+//   4. forward/backward at w_t on the same batch -> g_t, L_t   (multioptlrs.py:88),
+//   5. ratio history + per-parameter observation rows + reward + the 14 info statistics
+//      (utils/utils_env.py:155-164, utils/utils_common.py:188-196, multioptlrs.py:89-127),
+//   6. advances the env's minibatch cursor / epoch shuffle     (problems/optimize_nn.py:102-112),
+//   7. re-initialises the env if the episode ended             (vectorize/concurrentvecenv.py:32-38).
+// The first-layer matrix W1[D,N1] is streamed through a shared-memory tile; everything
+// else of the network ("tail": b1, W2, b2) is shared-memory resident.  All arithmetic fp32
+// (FFMA), statistics reduced in fp64.  See DESIGN.md for the data layout and traffic model.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "b200env.h"
+
+namespace {
+
+constexpr int RAW_DEPTH = 5;      // reference envs/multioptlrs.py:42
+constexpr int MAXI = 4;           // forward work items per warp
+constexpr int NSTAT = 8;
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_EVAL = 2 };
+enum { PASS_U = 0, PASS_G = 1, PASS_R = 2, PASS_E = 3 };
+enum { ST_ABSW = 0, ST_LR = 1, ST_LR2 = 2, ST_G = 3, ST_ABSADJG = 4, ST_GDIFF = 5, ST_STATE = 6 };
+
+struct EnvScalars {
+    double raw_gsum[RAW_DEPTH];
+    float raw_loss[RAW_DEPTH];
+    float adj_loss[B2E_MAX_HISTORY];
+    float loss_prev;
+    int raw_pos, head, nvalid, step, cursor, ord_sel, episode;
+};
+
+struct Dev {
+    int env_kind, kind, hidden;
+    int D, Dp, Ds, N1, N1p, C, Cp;
+    int P, Pp, P1, tailP, N, B, E, H, OD;
+    int max_batches, act_ver, rew_ver, obs_ver;
+    int KT, ntiles;
+    int nsc, ncc, nks, fitems;
+    int N1g, KR, gcc;
+    int row_lex, index_mode, auto_reset;
+    unsigned long long seed;
+    float lim1, lim2;
+    const float *X;
+    const int *labels;
+    const float *targets;
+    float *w, *gprev, *ringw, *ringg;
+    EnvScalars *sc;
+    int *ord;
+    const int *perm;
+    long long perm_stride;
+    const int *row_of_param;
+    int off_T, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
+        off_y, off_lb, off_misc;
+    int stage_stride, xslack;
+};
+
+struct StepArgs {
+    const float *actions;
+    const int *ext_idx;
+    const int *ext_cnt;
+    float *obs;
+    float *reward;
+    unsigned char *done;
+    double *info;
+    const unsigned char *mask;
+    const float *init_params;
+    float *grad_out;
+    float *loss_out;
+    int mode;
+};
+
+struct Stats {
+    double v[NSTAT];
+};
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ float nan_to_num_f(float x) {
+    if (x != x) return 0.0f;
+    if (isinf(x)) return copysignf(FLT_MAX, x);
+    return x;
+}
+__device__ __forceinline__ double nan_to_num_d(double x) {
+    if (x != x) return 0.0;
+    if (isinf(x)) return copysign(DBL_MAX, x);
+    return x;
+}
+__device__ __forceinline__ float clip_m1(float x) {          // multioptlrs.py:99
+    return fminf(fmaxf(nan_to_num_f(x), -100.0f), 100.0f) - 1.0f;
+}
+__device__ __forceinline__ float action_to_lr(float a, int ver) {   // utils_env.py:102-123
+    switch (ver) {
+        case 0: return exp10f(a - 4.0f);
+        case 1: return a * 1e-3f;
+        case 2: return exp2f(a);
+        default: return fmaxf((a + 1e3f) * 1e-6f, 0.0f);
+    }
+}
+__device__ __forceinline__ float glorot(unsigned long long seed, int e, int episode, int p,
+                                        float limit) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(p + 1);
+    z ^= ((unsigned long long)(unsigned)e << 32) | (unsigned)episode;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    float u = (float)((unsigned)(z >> 40)) * (1.0f / 16777216.0f);
+    return (2.0f * u - 1.0f) * limit;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block reduction of the per-thread statistics; result valid in thread 0
+__device__ void block_reduce(Stats &st, double *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = 0; i < NSTAT; ++i) {
+        double v = warp_sum(st.v[i]);
+        if (lane == 0) red[warp * NSTAT + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAT; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < nw; ++w) v += red[w * NSTAT + i];
+            st.v[i] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- minibatch gather
+__device__ void load_batch(const Dev &d, float *sm, const int *idx_g, int cnt) {
+    float *Xs = sm;
+    int *idx_s = reinterpret_cast<int *>(sm + d.off_idx);
+    for (int r = threadIdx.x; r < d.B; r += blockDim.x) idx_s[r] = (r < cnt) ? idx_g[r] : 0;
+    __syncthreads();
+    const int qrow = d.Ds >> 2, qdata = d.Dp >> 2;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int total = d.B * qrow + (d.xslack >> 2);          // + slack after the last row
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i / qrow, c = i - r * qrow;
+        float4 v = zero4;
+        if (r < cnt && c < qdata)
+            v = __ldg(reinterpret_cast<const float4 *>(d.X + (size_t)idx_s[r] * d.Dp) + c);
+        reinterpret_cast<float4 *>(Xs)[i] = v;
+    }
+    if (d.kind == B2E_PROBLEM_SOFTMAX) {
+        int *ys = reinterpret_cast<int *>(sm + d.off_y);
+        for (int r = threadIdx.x; r < d.B; r += blockDim.x)
+            ys[r] = (r < cnt) ? d.labels[idx_s[r]] : 0;
+    } else if (d.kind == B2E_PROBLEM_LINREG) {
+        float *yt = sm + d.off_y;
+        for (int i = threadIdx.x; i < d.B * d.C; i += blockDim.x) {
+            const int r = i / d.C, c = i - r * d.C;
+            yt[i] = (r < cnt) ? d.targets[(size_t)idx_s[r] * d.C + c] : 0.f;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------- forward pass
+// Hpre[s][c] += sum_{k in tile} Xs[s][k0+k] * T[k][c]; lane = sample, 8 columns per item.
+__device__ __forceinline__ void f_accumulate(const Dev &d, const float *Xs, const float *T,
+                                             int k0, int krows4, float (&acc)[MAXI][8]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int kslice = d.KT / d.nks;
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) {
+        const int it = warp + j * nw;
+        if (it < d.fitems) {
+            const int sc = it % d.nsc, rest = it / d.nsc;
+            const int cc = rest % d.ncc, ks = rest / d.ncc;
+            int s = sc * 32 + lane;
+            s = s < d.B ? s : d.B - 1;
+            const float *xrow = Xs + s * d.Ds + k0;
+            const float *tcol = T + cc * 8;
+            const int kb = ks * kslice;
+            int ke = kb + kslice;
+            ke = ke < krows4 ? ke : krows4;
+            for (int k = kb; k < ke; k += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(xrow + k);
+                const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float *t = tcol + (k + kk) * d.N1p;
+                    const float4 t0 = *reinterpret_cast<const float4 *>(t);
+                    const float4 t1 = *reinterpret_cast<const float4 *>(t + 4);
+                    acc[j][0] = fmaf(xv[kk], t0.x, acc[j][0]);
+                    acc[j][1] = fmaf(xv[kk], t0.y, acc[j][1]);
+                    acc[j][2] = fmaf(xv[kk], t0.z, acc[j][2]);
+                    acc[j][3] = fmaf(xv[kk], t0.w, acc[j][3]);
+                    acc[j][4] = fmaf(xv[kk], t1.x, acc[j][4]);
+                    acc[j][5] = fmaf(xv[kk], t1.y, acc[j][5]);
+                    acc[j][6] = fmaf(xv[kk], t1.z, acc[j][6]);
+                    acc[j][7] = fmaf(xv[kk], t1.w, acc[j][7]);
+                }
+            }
+        }
+    }
+}
+
+__device__ void f_store(const Dev &d, float *sm, float (&acc)[MAXI][8]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *Hb = sm + d.off_H;
+    float *red = sm + d.off_red;
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j) {
+        const int it = warp + j * nw;
+        if (it < d.fitems) {
+            const int sc = it % d.nsc, rest = it / d.nsc;
+            const int cc = rest % d.ncc, ks = rest / d.ncc;
+            const int s = sc * 32 + lane;
+            if (s < d.B) {
+                float *dst = (d.nks == 1 ? Hb : red + (size_t)ks * d.B * d.N1p) + s * d.N1p + cc * 8;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) dst[c] = acc[j][c];
+            }
+        }
+    }
+    __syncthreads();
+    if (d.nks > 1) {
+        const int n = d.B * d.N1p;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            float v = 0.f;
+            for (int ks = 0; ks < d.nks; ++ks) v += red[(size_t)ks * n + i];
+            Hb[i] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[MAXI][8]) {
+#pragma unroll
+    for (int j = 0; j < MAXI; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+}
+
+// copy W1 rows [k0, k0+krows) from HBM (natural, stride N1) into the tile (stride N1p);
+// rows up to krows4 are zero filled.
+__device__ void load_w_tile(const Dev &d, float *T, const float *wE, int k0, int krows,
+                            int krows4) {
+    if (d.N1p == d.N1) {
+        const int nq = (krows * d.N1) >> 2;
+        const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * d.N1);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x)
+            reinterpret_cast<float4 *>(T)[i] = src[i];
+    } else {
+        const int n = krows * d.N1;
+        const float *src = wE + (size_t)k0 * d.N1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int k = i / d.N1, c = i - k * d.N1;
+            T[k * d.N1p + c] = src[i];
+        }
+        for (int i = threadIdx.x; i < krows * (d.N1p - d.N1); i += blockDim.x) {
+            const int k = i / (d.N1p - d.N1), c = d.N1 + i - k * (d.N1p - d.N1);
+            T[k * d.N1p + c] = 0.f;
+        }
+    }
+    for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
+}
+
+// Hpre = X . W1 with W1 read from HBM
+__device__ void forward_from_global(const Dev &d, float *sm, const float *wE) {
+    float acc[MAXI][8];
+    zero_acc(acc);
+    float *T = sm + d.off_T;
+    for (int t = 0; t < d.ntiles; ++t) {
+        const int k0 = t * d.KT;
+        const int krows = min(d.KT, d.D - k0), krows4 = (krows + 3) & ~3;
+        load_w_tile(d, T, wE, k0, krows, krows4);
+        __syncthreads();
+        f_accumulate(d, sm, T, k0, krows4, acc);
+        __syncthreads();
+    }
+    f_store(d, sm, acc);
+}
+
+// ------------------------------------------------------------------ backward tile
+// T[k][c] = sum_s Xs[s][k0+k] * dPre[s][c] for the rows of one tile (lane = column).
+__device__ void g_compute(const Dev &d, const float *sm, float *T, int k0, int cnt) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float *Xs = sm;
+    const float *dP = sm + d.off_dP;
+    const int nitems = (d.KT / d.KR) * d.gcc;
+    for (int it = warp; it < nitems; it += nw) {
+        const int kc = it / d.gcc, c0 = (it - kc * d.gcc) * 32;
+        if (k0 + kc * d.KR >= d.D) continue;
+        const int r = lane / d.N1g, c = c0 + (lane & (d.N1g - 1));
+        const int kl = kc * d.KR + r * 8;
+        const int cc = c < d.N1p ? c : d.N1p - 1;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const float *xr = Xs + k0 + kl;
+        const float *dp = dP + cc;
+        for (int s = 0; s < cnt; ++s) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(xr + s * d.Ds);
+            const float4 x1 = *reinterpret_cast<const float4 *>(xr + s * d.Ds + 4);
+            const float dv = dp[s * d.N1p];
+            acc[0] = fmaf(x0.x, dv, acc[0]);
+            acc[1] = fmaf(x0.y, dv, acc[1]);
+            acc[2] = fmaf(x0.z, dv, acc[2]);
+            acc[3] = fmaf(x0.w, dv, acc[3]);
+            acc[4] = fmaf(x1.x, dv, acc[4]);
+            acc[5] = fmaf(x1.y, dv, acc[5]);
+            acc[6] = fmaf(x1.z, dv, acc[6]);
+            acc[7] = fmaf(x1.w, dv, acc[7]);
+        }
+        if (c < d.N1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (k0 + kl + j < d.D) T[(kl + j) * d.N1p + c] = acc[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------- the tail
+// Everything after the first matmul: bias/relu/second layer/softmax-CE (or MSE, or the
+// Rosenbrock function).  Fills dPre [B,N1p] and the tail gradient tg; returns mean loss.
+__device__ float tail_eval(const Dev &d, float *sm, int cnt) {
+    float *Hb = sm + d.off_H, *dP = sm + d.off_dP, *tw = sm + d.off_tw, *tg = sm + d.off_tg;
+    float *Zb = sm + d.off_Z, *lb = sm + d.off_lb, *misc = sm + d.off_misc;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (d.kind == B2E_PROBLEM_FUNC) {                 // utils/utils_functions.py:4-6
+        if (tid == 0) {
+            const float x = tw[0], y = tw[1], t = y - x * x;
+            misc[0] = 100.f * t * t + (1.f - x) * (1.f - x);
+            tg[0] = -400.f * x * t - 2.f * (1.f - x);
+            tg[1] = 200.f * t;
+        }
+        __syncthreads();
+        return misc[0];
+    }
+    const int N1 = d.N1, N1p = d.N1p, C = d.C;
+    const float *b1 = tw, *W2 = tw + N1, *b2 = tw + N1 + N1 * C;
+    float *Z = d.hidden ? Zb : Hb;
+    const int Zs = d.hidden ? d.Cp : N1p;
+    float *dZ = d.hidden ? Zb : dP;                   // dZ overwrites Z when hidden
+    if (d.hidden) {
+        for (int i = tid; i < cnt * N1; i += nt) {
+            const int s = i / N1, j = i - s * N1;
+            const float v = Hb[s * N1p + j] + b1[j];
+            Hb[s * N1p + j] = v > 0.f ? v : 0.f;
+        }
+        __syncthreads();
+        for (int i = tid; i < cnt * C; i += nt) {
+            const int s = i / C, c = i - s * C;
+            float z = b2[c];
+            for (int j = 0; j < N1; ++j) z = fmaf(Hb[s * N1p + j], W2[j * C + c], z);
+            Z[s * Zs + c] = z;
+        }
+    } else {
+        for (int i = tid; i < cnt * C; i += nt) {
+            const int s = i / C, c = i - s * C;
+            Z[s * Zs + c] += tw[c];
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < d.B; s += nt) {
+        float loss = 0.f;
+        if (s < cnt) {
+            const float *z = Z + s * Zs;
+            float *dz = dZ + s * Zs;
+            if (d.kind == B2E_PROBLEM_SOFTMAX) {
+                const int y = reinterpret_cast<const int *>(sm + d.off_y)[s];
+                float m = z[0];
+                for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) sum += expf(z[c] - m);
+                const float zy = z[y];
+                loss = (m + logf(sum)) - zy;
+                const float inv = 1.0f / sum;
+                for (int c = 0; c < C; ++c) {
+                    const float p = expf(z[c] - m) * inv;
+                    dz[c] = p - (c == y ? 1.f : 0.f);
+                }
+            } else {
+                const float *yt = sm + d.off_y + s * C;
+                for (int c = 0; c < C; ++c) {
+                    const float df = z[c] - yt[c];
+                    loss = fmaf(0.5f * df, df, loss);
+                    dz[c] = df;
+                }
+            }
+        } else {
+            for (int c = 0; c < C; ++c) dZ[s * Zs + c] = 0.f;
+        }
+        lb[s] = loss;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float l = 0.f;
+        for (int s = 0; s < cnt; ++s) l += lb[s];
+        misc[0] = l / (float)cnt;
+    }
+    if (d.hidden) {
+        float *gb1 = tg, *gW2 = tg + N1, *gb2 = tg + N1 + N1 * C;
+        for (int i = tid; i < N1 * C; i += nt) {
+            const int j = i / C, c = i - j * C;
+            float g = 0.f;
+            for (int s = 0; s < cnt; ++s) g = fmaf(Hb[s * N1p + j], dZ[s * Zs + c], g);
+            gW2[i] = g;
+        }
+        for (int c = tid; c < C; c += nt) {
+            float g = 0.f;
+            for (int s = 0; s < cnt; ++s) g += dZ[s * Zs + c];
+            gb2[c] = g;
+        }
+        for (int i = tid; i < d.B * N1; i += nt) {
+            const int s = i / N1, j = i - s * N1;
+            float v = 0.f;
+            if (s < cnt && Hb[s * N1p + j] > 0.f) {
+                for (int c = 0; c < C; ++c) v = fmaf(dZ[s * Zs + c], W2[j * C + c], v);
+            }
+            dP[s * N1p + j] = v;
+        }
+        __syncthreads();
+        for (int j = tid; j < N1; j += nt) {
+            float g = 0.f;
+            for (int s = 0; s < cnt; ++s) g += dP[s * N1p + j];
+            gb1[j] = g;
+        }
+    } else {
+        for (int c = tid; c < C; c += nt) {
+            float g = 0.f;
+            for (int s = 0; s < cnt; ++s) g += dP[s * N1p + c];
+            tg[c] = g;
+        }
+    }
+    __syncthreads();
+    return misc[0];
+}
+
+// ----------------------------------------------------------- elementwise epilogues
+struct EpiCtx {
+    int e;
+    int head_new, nvalid_new;
+    float *wE, *gE, *rwE, *rgE;      // this env's slices
+    const float *obsL;               // [H] clipped adjusted-loss columns
+};
+
+// Warp writes the staged observation rows of its 128-parameter chunk.
+__device__ __forceinline__ void emit_obs(const Dev &d, const StepArgs &a, const EpiCtx &cx,
+                                         const float *st, const int *rows_s, int pw0,
+                                         int lo, int hi, int soff) {
+    const int lane = threadIdx.x & 31;
+    const int OD = d.OD;
+    if (hi <= lo) return;
+    if (!d.row_lex) {
+        const size_t gb = ((size_t)cx.e * d.P + pw0) * OD;
+        const size_t g_lo = gb + (size_t)(lo - pw0) * OD, g_hi = gb + (size_t)(hi - pw0) * OD;
+        size_t b_lo = (g_lo + 3) & ~(size_t)3, b_hi = g_hi & ~(size_t)3;
+        if (b_lo >= b_hi) { b_lo = g_hi; b_hi = g_hi; }
+        for (size_t x = g_lo + lane; x < b_lo; x += 32) a.obs[x] = st[x - gb + soff];
+        for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128)
+            *reinterpret_cast<float4 *>(a.obs + x) =
+                *reinterpret_cast<const float4 *>(st + (x - gb + soff));
+        for (size_t x = b_hi + lane; x < g_hi; x += 32) a.obs[x] = st[x - gb + soff];
+    } else {
+        const int w_lo = (lo - pw0) * OD, w_hi = (hi - pw0) * OD;
+        float *base = a.obs + (size_t)cx.e * d.P * OD;
+        for (int wd = w_lo + lane; wd < w_hi; wd += 32) {
+            const int pl = wd / OD, col = wd - pl * OD;
+            base[(size_t)rows_s[pl] * OD + col] = st[soff + wd];
+        }
+    }
+}
+
+template <int PASS>
+__device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCtx &cx,
+                         int p_begin, int p_end, float *gsrc, bool tile_mode, int k0,
+                         Stats &st) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (p_end <= p_begin) return;
+    const int q0 = p_begin >> 2, q1 = (p_end + 3) >> 2;
+    const int nchunks = (q1 - q0 + 31) >> 5;
+    float *stage = sm + d.off_stage + warp * d.stage_stride;
+    int *rows_s = reinterpret_cast<int *>(sm + d.off_rows) + warp * 128;
+    const int H = d.H, OD = d.OD;
+    for (int ch = warp; ch < nchunks; ch += nw) {
+        const int p = (q0 + ch * 32 + lane) * 4;
+        const int pw0 = (q0 + ch * 32) * 4;
+        bool in[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) in[i] = (p + i >= p_begin) && (p + i < p_end);
+        const bool any = in[0] || in[1] || in[2] || in[3];
+        const bool all = in[0] && in[1] && in[2] && in[3];
+        int gi[4];
+        if (tile_mode) {
+            int k = p / d.N1, c = p - k * d.N1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                gi[i] = (k - k0) * d.N1p + c;
+                if (++c == d.N1) { c = 0; ++k; }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gi[i] = p + i - p_begin;
+        }
+        int rows[4] = {p, p + 1, p + 2, p + 3};
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (in[i]) g[i] = gsrc[gi[i]];
+            if (d.row_lex && (PASS == PASS_U || PASS == PASS_G)) {
+                const int4 r4 = *reinterpret_cast<const int4 *>(d.row_of_param + p);
+                rows[0] = r4.x; rows[1] = r4.y; rows[2] = r4.z; rows[3] = r4.w;
+            }
+        }
+        if (PASS == PASS_U) {
+            if (any) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(cx.wE + p);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                float wn[4], aw[4];
+                const float *act = a.actions + (size_t)cx.e * d.P;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float av = in[i] ? act[rows[i]] : 0.f;
+                    const float lr = action_to_lr(av, d.act_ver);
+                    wn[i] = fmaf(-g[i], lr, wv[i]);                 // multioptlrs.py:87
+                    aw[i] = nan_to_num_f(wn[i] / fabsf(wv[i]));     // utils_env.py:158-159
+                    if (in[i]) {
+                        st.v[ST_ABSW] += (double)fabsf(wn[i]);
+                        st.v[ST_LR] += (double)lr;
+                        st.v[ST_LR2] += (double)lr * (double)lr;
+                        gsrc[gi[i]] = wn[i];
+                    }
+                }
+                float *rw = cx.rwE + (size_t)cx.head_new * d.Pp + p;
+                if (all) {
+                    *reinterpret_cast<float4 *>(cx.wE + p) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+                    *reinterpret_cast<float4 *>(rw) = make_float4(aw[0], aw[1], aw[2], aw[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (in[i]) { cx.wE[p + i] = wn[i]; rw[i] = aw[i]; }
+                }
+            }
+        } else if (PASS == PASS_R || PASS == PASS_E) {
+            if (any) {
+                float *dst = (PASS == PASS_R) ? cx.gE + p : a.grad_out + (size_t)cx.e * d.P + p;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (in[i]) { dst[i] = g[i]; st.v[ST_G] += (double)g[i]; }
+            }
+        } else {   // PASS_G
+            // stage shift so that smem and global share their 16-byte phase
+            const int soff = d.row_lex ? 0 : (int)((((size_t)cx.e * d.P + pw0) * OD) & 3);
+            float *srow = stage + soff + (lane * 4) * OD;
+            if (any) {
+                const float4 gp4 = *reinterpret_cast<const float4 *>(cx.gE + p);
+                const float gp[4] = {gp4.x, gp4.y, gp4.z, gp4.w};
+                float ag[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ag[i] = nan_to_num_f(g[i] / fabsf(gp[i]));      // utils_env.py:156-157
+                    if (in[i]) {
+                        st.v[ST_G] += (double)g[i];
+                        st.v[ST_ABSADJG] += (double)fabsf(ag[i]);
+                        st.v[ST_GDIFF] += (double)fabsf(g[i] - gp[i]);
+                    }
+                }
+                float *rg = cx.rgE + (size_t)cx.head_new * d.Pp + p;
+                if (all) {
+                    *reinterpret_cast<float4 *>(cx.gE + p) = make_float4(g[0], g[1], g[2], g[3]);
+                    *reinterpret_cast<float4 *>(rg) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (in[i]) { cx.gE[p + i] = g[i]; rg[i] = ag[i]; }
+                }
+                // observation rows: [adj_w newest..oldest | adj_L | adj_g newest..oldest]
+                double sabs = 0.0;
+                for (int h = 0; h < H; ++h) {
+                    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = w4;
+                    if (h < cx.nvalid_new) {
+                        int slot = cx.head_new - h;
+                        slot += slot < 0 ? H : 0;
+                        w4 = *reinterpret_cast<const float4 *>(cx.rwE + (size_t)slot * d.Pp + p);
+                        if (h > 0)
+                            g4 = *reinterpret_cast<const float4 *>(cx.rgE + (size_t)slot * d.Pp + p);
+                        else
+                            g4 = make_float4(ag[0], ag[1], ag[2], ag[3]);
+                    }
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                    const float ol = cx.obsL[h];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (in[i]) sabs += (double)fabsf(wv[i]) + (double)fabsf(gv[i]);
+                        srow[i * OD + h] = clip_m1(wv[i]);
+                        srow[i * OD + H + h] = ol;
+                        srow[i * OD + 2 * H + h] = clip_m1(gv[i]);
+                    }
+                }
+                st.v[ST_STATE] += sabs;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rows_s[lane * 4 + i] = rows[i];
+            __syncwarp();
+            const int lo = max(pw0, p_begin), hi = min(pw0 + 128, p_end);
+            emit_obs(d, a, cx, stage, rows_s, pw0, lo, hi, soff);
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------- minibatch stream
+__device__ __forceinline__ const int *order_ptr(const Dev &d, int e, int sel) {
+    return d.ord + ((size_t)sel * d.E + e) * d.N;
+}
+
+// InMemoryDataSet.on_epoch_end with the env's fixed permutation: new[i] = old[perm[i]]
+__device__ void shuffle_order(const Dev &d, int e, EnvScalars *sc) {
+    const int sel = sc->ord_sel;
+    const int *src = order_ptr(d, e, sel);
+    int *dst = d.ord + ((size_t)(sel ^ 1) * d.E + e) * d.N;
+    const int *pm = d.perm + (size_t)e * d.perm_stride;
+    for (int i = threadIdx.x; i < d.N; i += blockDim.x) dst[i] = src[pm[i]];
+    __syncthreads();
+    if (threadIdx.x == 0) sc->ord_sel = sel ^ 1;
+    __syncthreads();
+}
+
+__device__ void current_batch(const Dev &d, const StepArgs &a, int e, const EnvScalars *sc,
+                              const int *&idx, int &cnt) {
+    if (d.kind == B2E_PROBLEM_FUNC) { idx = nullptr; cnt = 0; return; }
+    if (d.index_mode == B2E_INDEX_EXTERNAL) {
+        idx = a.ext_idx + (size_t)e * d.B;
+        cnt = a.ext_cnt[e];
+    } else {
+        const int lo = sc->cursor * d.B;
+        idx = order_ptr(d, e, sc->ord_sel) + lo;
+        cnt = min(d.B, d.N - lo);
+    }
+}
+
+__device__ void load_tail(const Dev &d, float *sm, const float *wE) {
+    float *tw = sm + d.off_tw;
+    for (int i = threadIdx.x; i < d.tailP; i += blockDim.x) tw[i] = wE[d.P1 + i];
+    __syncthreads();
+}
+
+// gradient of all parameters at the parameters currently in HBM / tw; PASS_R or PASS_E
+template <int PASS>
+__device__ float eval_current(const Dev &d, const StepArgs &a, float *sm, const EpiCtx &cx,
+                              int cnt, Stats &st) {
+    load_tail(d, sm, cx.wE);
+    if (d.ntiles) forward_from_global(d, sm, cx.wE);
+    const float loss = tail_eval(d, sm, cnt);
+    float *T = sm + d.off_T;
+    epilogue<PASS>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+    for (int t = 0; t < d.ntiles; ++t) {
+        const int k0 = t * d.KT;
+        g_compute(d, sm, T, k0, cnt);
+        __syncthreads();
+        epilogue<PASS>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
+        __syncthreads();
+    }
+    return loss;
+}
+
+__device__ void make_ctx(const Dev &d, int e, EpiCtx &cx) {
+    cx.e = e;
+    cx.wE = d.w + (size_t)e * d.Pp;
+    cx.gE = d.gprev + (size_t)e * d.Pp;
+    cx.rwE = d.ringw + (size_t)e * d.H * d.Pp;
+    cx.rgE = d.ringg + (size_t)e * d.H * d.Pp;
+    cx.head_new = 0;
+    cx.nvalid_new = 0;
+    cx.obsL = nullptr;
+}
+
+// base_reset (multioptlrs.py:66-78) of one env
+__device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
+    EnvScalars *sc = d.sc + e;
+    EpiCtx cx;
+    make_ctx(d, e, cx);
+    if (d.kind != B2E_PROBLEM_FUNC && d.index_mode == B2E_INDEX_INTERNAL) {
+        shuffle_order(d, e, sc);                                  // optimize_nn.py:114-120
+        if (threadIdx.x == 0) sc->cursor = 0;
+        __syncthreads();
+    }
+    const int *idx; int cnt;
+    current_batch(d, a, e, sc, idx, cnt);
+    if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
+    const int episode = sc->episode;
+    for (int p = threadIdx.x; p < d.Pp; p += blockDim.x) {
+        float v = 0.f;
+        if (p < d.P) {
+            if (a.init_params) v = a.init_params[(size_t)e * d.P + p];
+            else if (d.kind == B2E_PROBLEM_FUNC) v = p == 0 ? -1.9f : 2.0f;   // optimize_function.py:37
+            else if (p < d.P1) v = glorot(d.seed, e, episode, p, d.lim1);
+            else if (d.hidden && p >= d.P1 + d.N1 && p < d.P1 + d.N1 + d.N1 * d.C)
+                v = glorot(d.seed, e, episode, p, d.lim2);
+        }
+        cx.wE[p] = v;
+    }
+    __syncthreads();
+    Stats st;
+    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+    const float loss = eval_current<PASS_R>(d, a, sm, cx, cnt, st);
+    block_reduce(st, reinterpret_cast<double *>(sm + d.off_red));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
+        for (int i = 0; i < B2E_MAX_HISTORY; ++i) sc->adj_loss[i] = 0.f;
+        sc->raw_pos = 0;
+        sc->raw_loss[0] = loss;
+        sc->raw_gsum[0] = st.v[ST_G];
+        sc->loss_prev = loss;
+        sc->head = d.H - 1;
+        sc->nvalid = 0;
+        sc->step = 0;
+        sc->episode = episode + 1;
+    }
+    if (a.obs) {                                                  // obs = clip(0) - 1 = -1
+        float *o = a.obs + (size_t)e * d.P * d.OD;
+        const size_t n = (size_t)d.P * d.OD;
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = -1.0f;
+    }
+    __syncthreads();
+}
+
+__device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
+    EnvScalars *sc = d.sc + e;
+    EpiCtx cx;
+    make_ctx(d, e, cx);
+    float *misc = sm + d.off_misc;
+    float *T = sm + d.off_T;
+    const int *idx; int cnt;
+    current_batch(d, a, e, sc, idx, cnt);
+    if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
+    const int head_new = (sc->head + 1) % d.H;
+    const int nvalid_new = min(sc->nvalid + 1, d.H);
+    cx.head_new = head_new;
+    cx.nvalid_new = nvalid_new;
+    cx.obsL = misc + 8;
+    Stats st;
+    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+
+    // ---- gradient at w_{t-1}, update, forward at w_t (fused per tile)
+    load_tail(d, sm, cx.wE);
+    if (d.ntiles) forward_from_global(d, sm, cx.wE);
+    tail_eval(d, sm, cnt);
+    epilogue<PASS_U>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+    __syncthreads();
+    {   // tail: tg now holds w_t of the tail; make it the live tail parameters
+        float *tw = sm + d.off_tw, *tg = sm + d.off_tg;
+        for (int i = threadIdx.x; i < d.tailP; i += blockDim.x) tw[i] = tg[i];
+    }
+    float acc[MAXI][8];
+    zero_acc(acc);
+    for (int t = 0; t < d.ntiles; ++t) {
+        const int k0 = t * d.KT;
+        const int krows = min(d.KT, d.D - k0), krows4 = (krows + 3) & ~3;
+        g_compute(d, sm, T, k0, cnt);
+        __syncthreads();
+        epilogue<PASS_U>(d, a, sm, cx, k0 * d.N1, (k0 + krows) * d.N1, T, true, k0, st);
+        for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
+        if (d.N1p != d.N1)
+            for (int i = threadIdx.x; i < krows * (d.N1p - d.N1); i += blockDim.x) {
+                const int k = i / (d.N1p - d.N1), c = d.N1 + i - k * (d.N1p - d.N1);
+                T[k * d.N1p + c] = 0.f;
+            }
+        __syncthreads();
+        f_accumulate(d, sm, T, k0, krows4, acc);
+        __syncthreads();
+    }
+    if (d.ntiles) f_store(d, sm, acc);
+    __syncthreads();
+
+    // ---- gradient and loss at w_t
+    const float loss = tail_eval(d, sm, cnt);
+    if (threadIdx.x == 0) {
+        const double adjl = nan_to_num_d((double)loss / fabs((double)sc->loss_prev));
+        reinterpret_cast<double *>(misc + 2)[0] = adjl;          // misc[2..3]
+        float *obsL = misc + 8;
+        for (int h = 0; h < d.H; ++h) {
+            float v = 0.f;
+            if (h == 0) v = (float)adjl;
+            else if (h < nvalid_new) {
+                int slot = head_new - h;
+                slot += slot < 0 ? d.H : 0;
+                v = sc->adj_loss[slot];
+            }
+            obsL[h] = clip_m1(v);
+            misc[8 + B2E_MAX_HISTORY + h] = fabsf(v);
+        }
+    }
+    __syncthreads();
+    epilogue<PASS_G>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+    for (int t = 0; t < d.ntiles; ++t) {
+        const int k0 = t * d.KT;
+        g_compute(d, sm, T, k0, cnt);
+        __syncthreads();
+        epilogue<PASS_G>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
+        __syncthreads();
+    }
+    block_reduce(st, reinterpret_cast<double *>(sm + d.off_red));
+
+    // ---- scalars: reward, done, info, history bookkeeping (thread 0)
+    bool done = false;
+    if (threadIdx.x == 0) {
+        const double adjl = reinterpret_cast<double *>(misc + 2)[0];
+        const double L = (double)loss;
+        double reward;
+        switch (d.rew_ver) {                                       // utils_env.py:71-99
+            case 0: reward = -adjl; break;
+            case 1: reward = (double)(1.0f / loss); break;
+            case 2: reward = -adjl * 100.0; break;
+            case 3: reward = (double)(1.0f / loss) * 100.0; break;
+            case 4: reward = (double)logf(1.0f / loss); break;
+            case 5: reward = -(adjl - 1.0) * (adjl - 1.0); break;
+            default: reward = -(adjl - 1.0); break;
+        }
+        reward = fmin(fmax(reward, -100.0), 100.0);                // multioptlrs.py:103
+        const int step = sc->step + 1;                             // baseenvironment.py:37
+        done = step >= d.max_batches;
+        if (!done && loss > 1e4f) {                                // multioptlrs.py:105-107
+            done = true;
+            reward -= (double)(d.max_batches - step);
+        }
+        const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
+        sc->raw_pos = rp;
+        sc->raw_loss[rp] = loss;
+        sc->raw_gsum[rp] = st.v[ST_G];
+        sc->loss_prev = loss;
+        sc->adj_loss[head_new] = (float)adjl;
+        sc->head = head_new;
+        sc->nvalid = nvalid_new;
+        sc->step = step;
+        double gsum = 0.0, lsum = 0.0, labs = 0.0;
+        for (int i = 0; i < RAW_DEPTH; ++i) { gsum += sc->raw_gsum[i]; lsum += (double)sc->raw_loss[i]; }
+        for (int h = 0; h < d.H; ++h) labs += (double)misc[8 + B2E_MAX_HISTORY + h];
+        const double P = (double)d.P;
+        const double lr_mean = st.v[ST_LR] / P;
+        double lr_var = st.v[ST_LR2] / P - lr_mean * lr_mean;
+        lr_var = lr_var > 0.0 ? lr_var : 0.0;
+        const double ssum = st.v[ST_STATE] + P * labs;
+        double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
+        info[0] = done ? L : nan("");                              // multioptlrs.py:108-110
+        info[1] = L;
+        info[2] = st.v[ST_ABSW] / P;
+        info[3] = st.v[ST_ABSW];
+        info[4] = lr_mean;
+        info[5] = sqrt(lr_var);
+        info[6] = ssum / (P * (double)d.OD);
+        info[7] = ssum;
+        info[8] = gsum / (RAW_DEPTH * P);
+        info[9] = gsum;
+        info[10] = lsum / RAW_DEPTH;
+        info[11] = adjl;
+        info[12] = st.v[ST_ABSADJG] / P;
+        info[13] = st.v[ST_GDIFF] / P;
+        info[14] = reward;                                         // baseenvironment.py:40
+        info[15] = (double)step;
+        a.reward[e] = (float)reward;
+        a.done[e] = done ? 1 : 0;
+        misc[1] = done ? 1.f : 0.f;
+        if (d.kind != B2E_PROBLEM_FUNC && d.index_mode == B2E_INDEX_INTERNAL) {
+            const int cur = sc->cursor + 1;                        // optimize_nn.py:102-112
+            misc[4] = (cur * d.B >= d.N) ? 1.f : 0.f;
+            sc->cursor = (cur * d.B >= d.N) ? 0 : cur;
+        } else {
+            misc[4] = 0.f;
+        }
+    }
+    __syncthreads();
+    const bool wrap = misc[4] != 0.f;
+    done = misc[1] != 0.f;
+    __syncthreads();
+    if (wrap) shuffle_order(d, e, sc);
+    if (done && d.auto_reset) reset_env(d, a, sm, e);
+}
+
+__device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
+    EnvScalars *sc = d.sc + e;
+    EpiCtx cx;
+    make_ctx(d, e, cx);
+    const int *idx; int cnt;
+    current_batch(d, a, e, sc, idx, cnt);
+    if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
+    Stats st;
+    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+    const float loss = eval_current<PASS_E>(d, a, sm, cx, cnt, st);
+    if (threadIdx.x == 0) a.loss_out[e] = loss;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) optenv_kernel(const __grid_constant__ Dev d,
+                                                     const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    for (int e = blockIdx.x; e < d.E; e += gridDim.x) {
+        if (a.mode == MODE_STEP) {
+            step_env(d, a, sm, e);
+        } else if (a.mode == MODE_RESET) {
+            if (a.mask == nullptr || a.mask[e]) reset_env(d, a, sm, e);
+        } else {
+            eval_env(d, a, sm, e);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------ utility kernels
+__global__ void pad_rows_kernel(const float *src, float *dst, int n, int dcols, int dpad) {
+    const size_t total = (size_t)n * dpad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / dpad;
+        const int c = (int)(i - r * dpad);
+        dst[i] = c < dcols ? src[r * dcols + c] : 0.f;
+    }
+}
+
+__global__ void init_order_kernel(int *ord, const int *init, int e_count, int n) {
+    const size_t total = (size_t)e_count * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x)
+        ord[i] = init ? init[i] : (int)(i % n);
+}
+
+// ring <-> newest-first conversion for b2e_get_state / b2e_set_state
+__global__ void ring_copy_kernel(Dev d, int which, float *user, int to_user) {
+    const int e = blockIdx.x;
+    EnvScalars *sc = d.sc + e;
+    const int H = d.H;
+    if (which == B2E_STATE_ADJ_LOSSES) {
+        for (int h = threadIdx.x; h < H; h += blockDim.x) {
+            int slot = sc->head - h; slot += slot < 0 ? H : 0;
+            if (to_user) user[(size_t)e * H + h] = h < sc->nvalid ? sc->adj_loss[slot] : 0.f;
+            else sc->adj_loss[slot] = user[(size_t)e * H + h];
+        }
+        return;
+    }
+    float *ring = (which == B2E_STATE_ADJ_WEIGHTS ? d.ringw : d.ringg) + (size_t)e * H * d.Pp;
+    for (int h = 0; h < H; ++h) {
+        int slot = sc->head - h; slot += slot < 0 ? H : 0;
+        float *u = user + ((size_t)e * H + h) * d.P;
+        for (int p = threadIdx.x; p < d.P; p += blockDim.x) {
+            if (to_user) u[p] = h < sc->nvalid ? ring[(size_t)slot * d.Pp + p] : 0.f;
+            else ring[(size_t)slot * d.Pp + p] = u[p];
+        }
+    }
+}
+
+__global__ void scalars_copy_kernel(Dev d, int which, void *user, int to_user) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.E) return;
+    EnvScalars *sc = d.sc + e;
+    if (which == B2E_STATE_RAW_LOSSES || which == B2E_STATE_RAW_GSUMS) {
+        for (int i = 0; i < RAW_DEPTH; ++i) {
+            int slot = sc->raw_pos - i; slot += slot < 0 ? RAW_DEPTH : 0;
+            if (which == B2E_STATE_RAW_LOSSES) {
+                float *u = (float *)user + (size_t)e * RAW_DEPTH + i;
+                if (to_user) *u = sc->raw_loss[slot];
+                else { sc->raw_loss[slot] = *u; if (i == 0) sc->loss_prev = *u; }
+            } else {
+                double *u = (double *)user + (size_t)e * RAW_DEPTH + i;
+                if (to_user) *u = sc->raw_gsum[slot]; else sc->raw_gsum[slot] = *u;
+            }
+        }
+    } else if (which == B2E_STATE_STEP) {
+        int *u = (int *)user + e;
+        if (to_user) *u = sc->step; else sc->step = *u;
+    } else if (which == B2E_STATE_CURSOR) {
+        int *u = (int *)user + e;
+        if (to_user) *u = sc->cursor; else sc->cursor = *u;
+    }
+}
+
+// marks every adjusted-history slot valid (after b2e_set_state of a history)
+__global__ void set_nvalid_kernel(Dev d, int nvalid) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < d.E) d.sc[e].nvalid = nvalid;
+}
+
+__global__ void strided_copy_kernel(float *state, float *user, int e_count, int p, int pp,
+                                    int to_user) {
+    const size_t total = (size_t)e_count * p;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i / p, c = i - e * p;
+        if (to_user) user[i] = state[e * pp + c]; else state[e * pp + c] = user[i];
+    }
+}
+
+__global__ void order_copy_kernel(Dev d, int *user, int to_user) {
+    const int e = blockIdx.x;
+    int *cur = d.ord + ((size_t)d.sc[e].ord_sel * d.E + e) * d.N;
+    for (int i = threadIdx.x; i < d.N; i += blockDim.x) {
+        if (to_user) user[(size_t)e * d.N + i] = cur[i]; else cur[i] = user[(size_t)e * d.N + i];
+    }
+}
+
+__global__ void batch_indices_kernel(Dev d, int *idx_out, int *cnt_out) {
+    const int e = blockIdx.x;
+    const EnvScalars *sc = d.sc + e;
+    const int lo = sc->cursor * d.B;
+    const int cnt = min(d.B, d.N - lo);
+    const int *cur = d.ord + ((size_t)sc->ord_sel * d.E + e) * d.N + lo;
+    for (int r = threadIdx.x; r < d.B; r += blockDim.x) idx_out[(size_t)e * d.B + r] = r < cnt ? cur[r] : 0;
+    if (threadIdx.x == 0) cnt_out[e] = cnt;
+}
+
+__global__ void init_scalars_kernel(Dev d) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.E) return;
+    EnvScalars *sc = d.sc + e;
+    memset(sc, 0, sizeof(EnvScalars));
+    sc->head = d.H - 1;
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+// =============================================================== host side / C ABI
+struct b2e_env {
+    b2e_config cfg;
+    Dev d;
+    int nthreads, grid, num_sms;
+    size_t smem_bytes;
+    float *X, *targets_f;
+    int *labels, *ord, *perm, *row_of_param;
+    float *w, *gprev, *ringw, *ringg;
+    EnvScalars *sc;
+    bool dataset_bound, stream_bound;
+    int64_t launches;
+    std::string error;
+};
+
+namespace {
+
+int fail(b2e_handle h, const std::string &msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return 1;
+}
+
+#define CUDA_TRY(h, expr)                                                             \
+    do {                                                                              \
+        cudaError_t err__ = (expr);                                                   \
+        if (err__ != cudaSuccess)                                                     \
+            return fail(h, std::string(#expr) + ": " + cudaGetErrorString(err__));    \
+    } while (0)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+std::string lex_rows(int num_params, int *row_of_param_host) {
+    // row of parameter p = rank of the string "%d" % p among 0..P-1 (DFS over the digit trie
+    // enumerates them in lexicographic order).
+    int next_row = 0;
+    struct Frame { long long v; int digit; };
+    Frame *stack = new (std::nothrow) Frame[16];
+    if (!stack) return "out of memory";
+    // iterative pre-order: roots are 0..9 ("0" has no children)
+    for (int root = 0; root <= 9 && root < num_params; ++root) {
+        int depth = 0;
+        stack[0] = {root, 0};
+        row_of_param_host[root] = next_row++;
+        if (root == 0) continue;
+        while (depth >= 0) {
+            Frame &f = stack[depth];
+            if (f.digit > 9) { --depth; continue; }
+            const long long child = f.v * 10 + f.digit;
+            ++f.digit;
+            if (child >= num_params) { f.digit = 10; continue; }
+            row_of_param_host[child] = next_row++;
+            stack[++depth] = {child, 0};
+        }
+    }
+    delete[] stack;
+    return next_row == num_params ? "" : "internal error in lexicographic row table";
+}
+
+int configure(b2e_handle h) {
+    const b2e_config &c = h->cfg;
+    Dev &d = h->d;
+    memset(&d, 0, sizeof(d));
+    d.env_kind = c.env_kind;
+    d.kind = c.problem_kind;
+    d.hidden = c.num_hidden > 0;
+    d.E = c.num_envs; d.H = c.max_history; d.max_batches = c.max_batches;
+    d.act_ver = c.action_version; d.rew_ver = c.reward_version; d.obs_ver = c.observation_version;
+    d.row_lex = c.row_order == B2E_ROWS_LEXICOGRAPHIC;
+    d.index_mode = c.index_mode; d.auto_reset = c.auto_reset; d.seed = c.init_seed;
+    if (d.kind == B2E_PROBLEM_FUNC) {
+        d.D = 0; d.N1 = 8; d.C = 0; d.N = 0; d.B = 1; d.P1 = 0; d.tailP = 2; d.P = 2;
+    } else {
+        d.D = c.num_features; d.C = c.num_outputs; d.N = c.num_rows; d.B = c.batch_size;
+        d.N1 = d.hidden ? c.num_hidden : d.C;
+        d.P1 = d.D * d.N1;
+        d.tailP = d.hidden ? d.N1 + d.N1 * d.C + d.C : d.C;
+        d.P = d.P1 + d.tailP;
+        d.lim1 = sqrtf(6.0f / (float)(d.D + d.N1));
+        d.lim2 = d.hidden ? sqrtf(6.0f / (float)(d.N1 + d.C)) : 0.f;
+    }
+    d.Pp = round_up(d.P, 4);
+    d.OD = 3 * d.H;
+    d.Dp = round_up(d.D, 4);
+    d.Ds = d.Dp;
+    if (d.Ds > 0 && ((d.Ds >> 2) & 1) == 0) d.Ds += 4;       // odd number of float4 per row
+    d.N1p = round_up(d.N1, 8);
+    d.Cp = round_up(d.C > 0 ? d.C : 1, 4);
+    // backward decomposition: lane = column, N1g columns per lane group, 8 rows per lane
+    d.N1g = d.N1 >= 32 ? 32 : pow2_ceil(d.N1);
+    d.KR = 8 * (32 / d.N1g);
+    d.gcc = d.N1 > 32 ? (d.N1 + 31) / 32 : 1;
+    d.KT = d.KR > 64 ? d.KR : 64;
+    d.ntiles = d.D > 0 ? (d.D + d.KT - 1) / d.KT : 0;
+    // threads: small problems use small CTAs so that several fit one SM
+    const long long work = (long long)d.P;
+    h->nthreads = work >= 4096 ? 256 : (work >= 512 ? 128 : 64);
+    int nw = h->nthreads / 32;
+    // forward decomposition
+    d.nsc = (d.B + 31) / 32;
+    d.ncc = d.N1p / 8;
+    while (d.nsc * d.ncc > nw * MAXI && h->nthreads < 512) { h->nthreads *= 2; nw *= 2; }
+    if (d.nsc * d.ncc > nw * MAXI)
+        return fail(h, "batch_size x layer width too large for the fused kernel "
+                       "(need ceil(B/32) * ceil(N1/8) <= 64)");
+    d.nks = 1;
+    while (d.nsc * d.ncc * d.nks * 2 <= nw && d.KT / (d.nks * 2) >= 4) d.nks *= 2;
+    d.fitems = d.nsc * d.ncc * d.nks;
+    // shared memory carve-up (float offsets, all multiples of 4)
+    d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
+    int off = d.B * d.Ds + d.xslack;
+    d.off_T = off; off += d.KT * d.N1p;
+    d.off_H = off; off += round_up(d.B * d.N1p, 4);
+    d.off_dP = off; off += round_up(d.B * d.N1p, 4);
+    d.off_tw = off; off += round_up(d.tailP, 4);
+    d.off_tg = off; off += round_up(d.tailP, 4);
+    d.off_Z = off; off += d.hidden ? round_up(d.B * d.Cp, 4) : 0;
+    const int red_floats = 2 * NSTAT * 16;
+    const int fred = d.nks > 1 ? d.nks * d.B * d.N1p : 0;
+    d.off_red = off; off += round_up(fred > red_floats ? fred : red_floats, 4);
+    d.stage_stride = round_up(128 * d.OD + 4, 4);
+    d.off_stage = off; off += nw * d.stage_stride;
+    d.off_rows = off; off += nw * 128;
+    d.off_idx = off; off += round_up(d.B, 4);
+    d.off_y = off; off += round_up(d.B * (d.kind == B2E_PROBLEM_LINREG ? d.C : 1), 4);
+    d.off_lb = off; off += round_up(d.B, 4);
+    d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
+    h->smem_bytes = (size_t)off * sizeof(float);
+    return 0;
+}
+
+int launch(b2e_handle h, const StepArgs &args, void *stream) {
+    optenv_kernel<<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2e_abi_version(void) { return B2E_ABI_VERSION; }
+
+const char *b2e_last_error(b2e_handle h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int64_t b2e_launch_count(b2e_handle h) { return h ? h->launches : 0; }
+
+int b2e_num_params(b2e_handle h) { return h ? h->d.P : -1; }
+
+int b2e_obs_dim(b2e_handle h) { return h ? h->d.OD : -1; }
+
+int b2e_create(const b2e_config *cfg, b2e_handle *out) {
+    if (!cfg || !out) return fail(nullptr, "b2e_create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(b2e_config))
+        return fail(nullptr, "b2e_create: b2e_config.struct_size mismatch (ABI skew)");
+    if (cfg->env_kind != B2E_ENV_MULTIOPTLRS)
+        return fail(nullptr, "b2e_create: env_kind not supported (MultiOptLRs only in this build)");
+    if (cfg->history_version != 3 || cfg->observation_version != 3)
+        return fail(nullptr, "b2e_create: MultiOptLRs is history_version 3 / observation_version 3 "
+                             "(reference envs/multioptlrs.py:61)");
+    if (cfg->action_version < 0 || cfg->action_version > 3 || cfg->reward_version < 0 ||
+        cfg->reward_version > 6)
+        return fail(nullptr, "b2e_create: bad action/reward version (RuntimeError in the reference)");
+    if (cfg->problem_kind < 0 || cfg->problem_kind > 2) return fail(nullptr, "Not a name of a problem.");
+    if (cfg->num_envs < 1 || cfg->max_history < 1 || cfg->max_history > B2E_MAX_HISTORY ||
+        cfg->max_batches < 1)
+        return fail(nullptr, "b2e_create: num_envs/max_history/max_batches out of range");
+    if (cfg->problem_kind != B2E_PROBLEM_FUNC &&
+        (cfg->num_features < 1 || cfg->num_outputs < 1 || cfg->num_rows < 1 || cfg->batch_size < 1 ||
+         cfg->batch_size > cfg->num_rows || cfg->num_hidden < 0))
+        return fail(nullptr, "b2e_create: bad problem shape");
+    if (cfg->problem_kind == B2E_PROBLEM_LINREG && cfg->num_hidden != 0)
+        return fail(nullptr, "b2e_create: linreg has no hidden layer");
+    if (cfg->auto_reset && cfg->index_mode == B2E_INDEX_EXTERNAL && cfg->problem_kind != B2E_PROBLEM_FUNC)
+        return fail(nullptr, "b2e_create: auto_reset needs the internal index stream");
+    b2e_handle h = new (std::nothrow) b2e_env();
+    if (!h) return fail(nullptr, "b2e_create: out of host memory");
+    h->cfg = *cfg;
+    h->launches = 0;
+    h->dataset_bound = h->stream_bound = false;
+    h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = nullptr;
+    h->w = h->gprev = h->ringw = h->ringg = nullptr; h->sc = nullptr;
+    auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return bail("b2e_create: cudaSetDevice failed");
+    if (configure(h)) return bail(h->error);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail("cudaGetDeviceProperties failed");
+    h->num_sms = prop.multiProcessorCount;
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return bail("b2e_create: problem does not fit the fused kernel's shared memory (" +
+                    std::to_string(h->smem_bytes) + " bytes needed)");
+    if (cudaFuncSetAttribute(optenv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)h->smem_bytes) != cudaSuccess)
+        return bail("b2e_create: cudaFuncSetAttribute(smem) failed");
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel, h->nthreads,
+                                                      h->smem_bytes) != cudaSuccess || occ < 1)
+        return bail("b2e_create: kernel does not fit an SM");
+    const long long resident = (long long)occ * h->num_sms;
+    h->grid = (int)(cfg->num_envs < resident ? cfg->num_envs : resident);
+    Dev &d = h->d;
+    const size_t EP = (size_t)d.E * d.Pp;
+    auto dmalloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
+    if (!dmalloc((void **)&h->w, EP * 4) || !dmalloc((void **)&h->gprev, EP * 4) ||
+        !dmalloc((void **)&h->ringw, EP * d.H * 4) || !dmalloc((void **)&h->ringg, EP * d.H * 4) ||
+        !dmalloc((void **)&h->sc, (size_t)d.E * sizeof(EnvScalars)))
+        return bail("b2e_create: cudaMalloc of env state failed");
+    cudaMemset(h->w, 0, EP * 4); cudaMemset(h->gprev, 0, EP * 4);
+    cudaMemset(h->ringw, 0, EP * d.H * 4); cudaMemset(h->ringg, 0, EP * d.H * 4);
+    if (d.kind != B2E_PROBLEM_FUNC) {
+        if (!dmalloc((void **)&h->X, (size_t)d.N * d.Dp * 4) ||
+            !dmalloc((void **)&h->labels, (size_t)d.N * 4) ||
+            !dmalloc((void **)&h->targets_f, (size_t)d.N * d.C * 4))
+            return bail("b2e_create: cudaMalloc of the data set failed");
+        if (d.index_mode == B2E_INDEX_INTERNAL) {
+            if (!dmalloc((void **)&h->ord, (size_t)2 * d.E * d.N * 4) ||
+                !dmalloc((void **)&h->perm, (size_t)d.E * d.N * 4))
+                return bail("b2e_create: cudaMalloc of the index stream failed");
+        }
+    }
+    if (d.row_lex) {
+        int *rows = new (std::nothrow) int[d.Pp];
+        if (!rows) return bail("b2e_create: out of host memory");
+        for (int i = 0; i < d.Pp; ++i) rows[i] = 0;
+        const std::string err = lex_rows(d.P, rows);
+        bool ok = err.empty() && dmalloc((void **)&h->row_of_param, (size_t)d.Pp * 4) &&
+                  cudaMemcpy(h->row_of_param, rows, (size_t)d.Pp * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        delete[] rows;
+        if (!ok) return bail("b2e_create: row table: " + err);
+    }
+    d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
+    d.w = h->w; d.gprev = h->gprev; d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
+    d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param;
+    init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
+    *out = h;
+    return 0;
+}
+
+void b2e_destroy(b2e_handle h) {
+    if (!h) return;
+    cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
+    cudaFree(h->row_of_param); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
+    cudaFree(h->ringg); cudaFree(h->sc);
+    delete h;
+}
+
+int b2e_bind_dataset(b2e_handle h, const float *features, const void *targets, void *stream) {
+    if (!h) return 1;
+    Dev &d = h->d;
+    if (d.kind == B2E_PROBLEM_FUNC) return fail(h, "b2e_bind_dataset: the func problem has no data");
+    if (!features || !targets) return fail(h, "b2e_bind_dataset: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    pad_rows_kernel<<<1184, 256, 0, s>>>(features, h->X, d.N, d.D, d.Dp);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    if (d.kind == B2E_PROBLEM_SOFTMAX)
+        CUDA_TRY(h, cudaMemcpyAsync(h->labels, targets, (size_t)d.N * 4, cudaMemcpyDeviceToDevice, s));
+    else
+        CUDA_TRY(h, cudaMemcpyAsync(h->targets_f, targets, (size_t)d.N * d.C * 4, cudaMemcpyDeviceToDevice, s));
+    h->dataset_bound = true;
+    return 0;
+}
+
+int b2e_set_index_stream(b2e_handle h, const int32_t *perms, int per_env,
+                         const int32_t *init_orders, void *stream) {
+    if (!h) return 1;
+    Dev &d = h->d;
+    if (d.kind == B2E_PROBLEM_FUNC || d.index_mode != B2E_INDEX_INTERNAL)
+        return fail(h, "b2e_set_index_stream: handle has no internal index stream");
+    if (!perms) return fail(h, "b2e_set_index_stream: null perms");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = (size_t)(per_env ? d.E : 1) * d.N * 4;
+    CUDA_TRY(h, cudaMemcpyAsync(h->perm, perms, bytes, cudaMemcpyDeviceToDevice, s));
+    d.perm_stride = per_env ? d.N : 0;
+    init_order_kernel<<<1184, 256, 0, s>>>(h->ord, init_orders, d.E, d.N);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    h->stream_bound = true;
+    return 0;
+}
+
+static int check_ready(b2e_handle h, const int32_t *idx, const int32_t *cnt) {
+    const Dev &d = h->d;
+    if (d.kind == B2E_PROBLEM_FUNC) return 0;
+    if (!h->dataset_bound) return fail(h, "no data set bound (b2e_bind_dataset)");
+    if (d.index_mode == B2E_INDEX_INTERNAL) {
+        if (!h->stream_bound) return fail(h, "no index stream set (b2e_set_index_stream)");
+    } else if (!idx || !cnt) {
+        return fail(h, "external index mode: batch_idx / batch_cnt are required");
+    }
+    return 0;
+}
+
+int b2e_reset(b2e_handle h, const uint8_t *env_mask, const float *init_params,
+              const int32_t *batch_idx, const int32_t *batch_cnt, float *obs_out, void *stream) {
+    if (!h) return 1;
+    if (check_ready(h, batch_idx, batch_cnt)) return 1;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = MODE_RESET; a.mask = env_mask; a.init_params = init_params;
+    a.ext_idx = batch_idx; a.ext_cnt = batch_cnt; a.obs = obs_out;
+    return launch(h, a, stream);
+}
+
+int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
+             const int32_t *batch_cnt, float *obs_out, float *reward_out, uint8_t *done_out,
+             double *info_out, void *stream) {
+    if (!h) return 1;
+    if (!actions || !obs_out || !reward_out || !done_out || !info_out)
+        return fail(h, "b2e_step: null pointer");
+    if (check_ready(h, batch_idx, batch_cnt)) return 1;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = MODE_STEP; a.actions = actions; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
+    a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out;
+    return launch(h, a, stream);
+}
+
+int b2e_eval(b2e_handle h, const int32_t *batch_idx, const int32_t *batch_cnt, float *grad_out,
+             float *loss_out, void *stream) {
+    if (!h) return 1;
+    if (!grad_out || !loss_out) return fail(h, "b2e_eval: null pointer");
+    if (check_ready(h, batch_idx, batch_cnt)) return 1;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = MODE_EVAL; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
+    a.grad_out = grad_out; a.loss_out = loss_out;
+    return launch(h, a, stream);
+}
+
+static int state_io(b2e_handle h, int which, void *user, size_t bytes, void *stream, int to_user) {
+    if (!h) return 1;
+    if (!user) return fail(h, "b2e_get/set_state: null pointer");
+    Dev &d = h->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t want = 0;
+    switch (which) {
+        case B2E_STATE_PARAMS: case B2E_STATE_GRAD_PREV: want = (size_t)d.E * d.P * 4; break;
+        case B2E_STATE_ADJ_WEIGHTS: case B2E_STATE_ADJ_GRADS: want = (size_t)d.E * d.H * d.P * 4; break;
+        case B2E_STATE_ADJ_LOSSES: want = (size_t)d.E * d.H * 4; break;
+        case B2E_STATE_RAW_LOSSES: want = (size_t)d.E * RAW_DEPTH * 4; break;
+        case B2E_STATE_RAW_GSUMS: want = (size_t)d.E * RAW_DEPTH * 8; break;
+        case B2E_STATE_STEP: case B2E_STATE_CURSOR: want = (size_t)d.E * 4; break;
+        case B2E_STATE_ORDER: want = (size_t)d.E * d.N * 4; break;
+        default: return fail(h, "b2e_get/set_state: unknown selector");
+    }
+    if (bytes != want)
+        return fail(h, "b2e_get/set_state: buffer is " + std::to_string(bytes) + " bytes, expected " +
+                           std::to_string(want));
+    switch (which) {
+        case B2E_STATE_PARAMS: case B2E_STATE_GRAD_PREV:
+            strided_copy_kernel<<<1184, 256, 0, s>>>(which == B2E_STATE_PARAMS ? h->w : h->gprev,
+                                                     (float *)user, d.E, d.P, d.Pp, to_user);
+            break;
+        case B2E_STATE_ADJ_WEIGHTS: case B2E_STATE_ADJ_GRADS: case B2E_STATE_ADJ_LOSSES:
+            if (!to_user) set_nvalid_kernel<<<(d.E + 127) / 128, 128, 0, s>>>(d, d.H);
+            ring_copy_kernel<<<d.E, 256, 0, s>>>(d, which, (float *)user, to_user);
+            break;
+        case B2E_STATE_ORDER:
+            if (!h->ord) return fail(h, "b2e_get/set_state: no internal index stream");
+            order_copy_kernel<<<d.E, 256, 0, s>>>(d, (int *)user, to_user);
+            break;
+        default:
+            scalars_copy_kernel<<<(d.E + 127) / 128, 128, 0, s>>>(d, which, user, to_user);
+    }
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int b2e_get_state(b2e_handle h, int which, void *dst, size_t bytes, void *stream) {
+    return state_io(h, which, dst, bytes, stream, 1);
+}
+
+int b2e_set_state(b2e_handle h, int which, const void *src, size_t bytes, void *stream) {
+    return state_io(h, which, const_cast<void *>(src), bytes, stream, 0);
+}
+
+int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void *stream) {
+    if (!h) return 1;
+    if (!idx_out || !cnt_out) return fail(h, "b2e_get_batch_indices: null pointer");
+    if (!h->ord || !h->stream_bound) return fail(h, "b2e_get_batch_indices: no internal index stream");
+    batch_indices_kernel<<<h->d.E, 64, 0, (cudaStream_t)stream>>>(h->d, idx_out, cnt_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

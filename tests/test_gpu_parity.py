@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Protocol (BASELINE.json north_star): per step, from identical states and host-supplied
+minibatch indices; index/sampling streams bit-exact; losses, gradients, new weights,
+observations, rewards within 1e-5 relative (fp32); done flags exact.
+
+Tolerances, stated once:
+* RTOL = 1e-5 relative to max(|reference|, SCALE) where SCALE is the natural magnitude of
+  the quantity (1 for observation ratios, the batch's sum of absolute terms for sum-type
+  quantities such as gradients and the signed grads_sum statistic).  fp32 dot products of
+  32..784 terms carry ~1e-7 * sum|terms| of rounding noise, so an element whose terms
+  cancel cannot be compared relative to its own (tiny) magnitude.
+* Observation columns are ratios x_t/|x_{t-1}|; their error is the numerator's error
+  divided by |x_{t-1}|.  Elements whose denominator is itself below 1e-3 of the tensor's
+  RMS (ill conditioned, e.g. a gradient component that happens to vanish) are compared
+  after the +-100 clip with an absolute 1e-2 window; everything else at RTOL.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import optenv_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'optlrs_*.npz')))
+
+
+def _mods():
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    return BatchedOptEnv, ProblemSpec
+
+
+def make_data(spec, num_rows, seed=0):
+    rng = np.random.RandomState(seed)
+    feats = rng.uniform(size=(num_rows, spec.num_features))
+    feats = ((feats - feats.min(0)) / (feats.max(0) - feats.min(0) + 1e-8)).astype(np.float32)
+    if spec.kind == 'softmax':
+        targs = rng.randint(0, spec.num_outputs, size=num_rows).astype(np.int32)
+    else:
+        true_w = rng.normal(size=(spec.num_features, spec.num_outputs))
+        targs = (feats @ true_w + 0.1 * rng.normal(size=(num_rows, spec.num_outputs))).astype(np.float32)
+    return feats, targs
+
+
+def rel_err(actual, ref, scale):
+    return np.abs(actual - ref) / np.maximum(np.abs(ref), scale)
+
+
+def check_obs(obs, ref_obs, ill, tag):
+    """obs/ref_obs [E,P,3H] natural order; ``ill`` marks ill-conditioned ratio entries."""
+    err = np.abs(obs - ref_obs) / np.maximum(1.0, np.abs(ref_obs + 1.0))
+    good = ~ill
+    assert np.all(err[good] <= 20 * RTOL), (tag, float(err[good].max()))
+    assert np.mean(err[good] <= RTOL) > 0.98, (tag, float(np.mean(err[good] <= RTOL)))
+    if ill.any():
+        assert np.all(err[ill] <= 1e-2), (tag, float(err[ill].max()))
+
+
+def shift_ill(ill, depth, new_w, new_g):
+    """History shift of the ill-conditioning mask: columns [w(H) | L(H) | g(H)]."""
+    out = np.zeros_like(ill)
+    out[:, :, 1:depth] = ill[:, :, 0:depth - 1]
+    out[:, :, 2 * depth + 1:3 * depth] = ill[:, :, 2 * depth:3 * depth - 1]
+    out[:, :, 0] = new_w
+    out[:, :, 2 * depth] = new_g
+    return out
+
+
+SPECS = {
+    'iris_softmax': (orc.ProblemSpec('softmax', 4, (), 3), 150, 32, 6),
+    'mlp_small': (orc.ProblemSpec('softmax', 6, (5,), 3), 50, 16, 3),
+    'linreg': (orc.ProblemSpec('linreg', 4, (), 1), 150, 32, 2),
+    'softmax_784x10': (orc.ProblemSpec('softmax', 784, (), 10), 600, 32, 3),
+    'mlp_784x64x10': (orc.ProblemSpec('softmax', 784, (64,), 10), 600, 32, 3),
+    'odd_shapes': (orc.ProblemSpec('softmax', 49, (10,), 7), 101, 20, 2),
+    'func': (orc.ProblemSpec('func', 0, (), 0), 0, None, 4),
+}
+
+
+def product_spec(spec):
+    _, ProblemSpec = _mods()
+    return ProblemSpec(spec.kind, spec.num_features, tuple(spec.hidden), spec.num_outputs)
+
+
+@pytest.mark.parametrize('name', [k for k in SPECS if k != 'func'])
+def test_loss_and_gradient_match_oracle(name):
+    """BaseProblem.get(): loss and batch-SUM gradient, ragged batches included."""
+    BatchedOptEnv, _ = _mods()
+    spec, num_rows, batch, num_envs = SPECS[name]
+    feats, targs = make_data(spec, num_rows)
+    rng = np.random.RandomState(1)
+    env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch,
+                        index_mode='external', auto_reset=False)
+    params = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
+    params += 0.05 * rng.normal(size=params.shape).astype(np.float32)
+    env.set_state('params', params)
+    idx = rng.randint(0, num_rows, size=(num_envs, batch)).astype(np.int32)
+    cnt = np.full(num_envs, batch, np.int32)
+    cnt[-1] = max(1, batch // 3)                       # ragged last batch
+    grad, loss = env.evaluate(idx, cnt)
+    grad, loss = grad.cpu().numpy(), loss.cpu().numpy()
+    mask = np.arange(batch)[None, :] < cnt[:, None]
+    ref_g, ref_l = orc.loss_and_grad(spec, params, feats[idx], targs[idx], mask)
+    abs_g, _ = orc.loss_and_grad(spec, np.abs(params), np.abs(feats[idx]), targs[idx], mask)
+    scale = np.maximum(np.abs(ref_g).mean(axis=1, keepdims=True), 1e-30)
+    assert rel_err(loss, ref_l, 1e-30).max() <= RTOL, rel_err(loss, ref_l, 1e-30).max()
+    err = rel_err(grad, ref_g, scale)
+    assert err.max() <= RTOL, (name, float(err.max()))
+    env.close()
+
+
+@pytest.mark.parametrize('row_order', ['lexicographic', 'natural'])
+@pytest.mark.parametrize('name', list(SPECS))
+def test_step_parity_from_identical_states(name, row_order):
+    """Per-step parity with host-supplied minibatch indices (external index mode)."""
+    BatchedOptEnv, _ = _mods()
+    spec, num_rows, batch, num_envs = SPECS[name]
+    func = spec.kind == 'func'
+    feats, targs = (None, None) if func else make_data(spec, num_rows)
+    rng = np.random.RandomState(2)
+    max_batches, depth = 7, 5
+    env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch,
+                        max_batches=max_batches, max_history=depth, row_order=row_order,
+                        index_mode='external', auto_reset=False)
+    ref = orc.BatchedOptEnvOracle(spec, feats, targs, num_envs, batch_size=batch,
+                                  config=orc.EnvConfig.multioptlrs(max_batches, depth),
+                                  perms=None if func else np.tile(np.arange(num_rows), (num_envs, 1)))
+    num_params = ref.num_params
+    perm = orc.lexicographic_rows(num_params) if row_order == 'lexicographic' else np.arange(num_params)
+    bsz = 1 if func else batch
+
+    def draw_batch():
+        if func:
+            return None, None
+        idx = rng.randint(0, num_rows, size=(num_envs, bsz)).astype(np.int32)
+        cnt = np.full(num_envs, bsz, np.int32)
+        cnt[rng.randint(num_envs)] = rng.randint(1, bsz + 1)
+        return idx, cnt
+
+    init = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
+    idx, cnt = draw_batch()
+    if not func:
+        ref.set_batch(idx, cnt)
+    ref_obs = ref.reset(init_params=init)
+    obs = env.reset(init_params=init, batch_idx=idx, batch_cnt=cnt).cpu().numpy()
+    assert np.array_equal(obs.reshape(num_envs, num_params, -1)[:, np.argsort(perm)],
+                          ref_obs.astype(np.float32))
+    ill = np.zeros((num_envs, num_params, 3 * depth), bool)
+    for t in range(max_batches):
+        idx, cnt = draw_batch()
+        if not func:
+            ref.set_batch(idx, cnt)
+        lo, hi = (-1.0, 1.5) if func else (0.0, 3.0)
+        actions_nat = rng.uniform(lo, hi, size=(num_envs, num_params)).astype(np.float32)
+        prev_w = ref.weights.astype(np.float64).copy()
+        prev_g = ref.raw_g[0].copy()
+        ref_obs, ref_rew, ref_done, ref_info = ref.step(actions_nat)
+        rows = actions_nat[:, perm].reshape(-1)
+        obs, rew, done, info = env.step(torch.as_tensor(rows, device=env.device), idx, cnt)
+        obs = obs.cpu().numpy().reshape(num_envs, num_params, -1)
+        obs_nat = np.empty_like(obs)
+        obs_nat[:, perm] = obs
+        tag = (name, row_order, t)
+        assert np.array_equal(done.cpu().numpy().astype(bool), ref_done), tag
+        # a ratio x_t/|x_{t-1}| is ill conditioned when both are tiny next to the tensor's RMS
+        new_g = ref.raw_g[0]
+        g_rms = np.sqrt(np.mean(new_g ** 2, axis=1, keepdims=True)) + 1e-30
+        w_rms = np.sqrt(np.mean(prev_w ** 2, axis=1, keepdims=True)) + 1e-30
+        ill = shift_ill(ill, depth,
+                        np.maximum(np.abs(prev_w), np.abs(ref.weights)) < 1e-2 * w_rms,
+                        np.maximum(np.abs(prev_g), np.abs(new_g)) < 1e-2 * g_rms)
+        check_obs(obs_nat, ref_obs, ill, tag)
+        np.testing.assert_allclose(rew.cpu().numpy(), ref_rew, rtol=RTOL, atol=RTOL, err_msg=str(tag))
+        new_w = env.get_state('params').cpu().numpy()
+        werr = rel_err(new_w, ref.weights, np.abs(ref.weights).mean())
+        assert werr.max() <= RTOL, (tag, float(werr.max()))
+        got = env.info_dict(info)
+        gabs = np.abs(ref.raw_g).sum(axis=(0, 2))
+        for key in orc.INFO_KEYS:
+            want = ref_info[key]
+            if key in ('states_mean', 'states_sum'):
+                finite = np.abs(ref_obs + 1).max(axis=(1, 2)) < 99.0     # no clipped ratio
+                np.testing.assert_allclose(got[key][finite], want[finite], rtol=1e-4, err_msg=str(tag + (key,)))
+                continue
+            scale = {'grads_sum': gabs, 'grads_mean': gabs / (5 * num_params)}.get(key, 1e-30)
+            err = rel_err(got[key], want, scale)
+            err = np.where(np.isnan(want) & np.isnan(got[key]), 0.0, err)
+            tol = 1e-4 if key in ('actions_std', 'adjusted_grad') else RTOL
+            assert np.all(err <= tol), (tag, key, got[key], want)
+        assert np.array_equal(got['episode_l'], ref.current_step), tag
+        # keep both sides on IDENTICAL states for the next step
+        ref.weights = new_w.copy()
+        ref.raw_w[0] = new_w
+        g_dev = env.get_state('grad_prev').cpu().numpy().astype(np.float64)
+        ref.raw_g[0] = g_dev
+    env.close()
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_reference_runs_on_device(path):
+    """The fixtures recorded from the reference's own env code, replayed on the GPU with the
+    on-device minibatch stream: index stream bit-exact, outputs within fp32 tolerance."""
+    BatchedOptEnv, _ = _mods()
+    fix = dict(np.load(path, allow_pickle=False))
+    kwargs = dict(zip([str(k) for k in fix['env_kwargs_keys']], [int(v) for v in fix['env_kwargs_vals']]))
+    spec = orc.ProblemSpec(str(fix['problem_kind']), int(fix['num_features']),
+                           tuple(int(h) for h in fix['hidden']), int(fix['num_outputs']))
+    num_envs = int(fix['num_envs'])
+    func = spec.kind == 'func'
+    batch = None if func or int(fix['batch_size']) < 0 else int(fix['batch_size'])
+    env = BatchedOptEnv(product_spec(spec), None if func else fix['feats'],
+                        None if func else fix['labels'], num_envs, batch_size=batch,
+                        perms=None if func else fix['perms'],
+                        init_orders=None if func else fix['init_orders'], auto_reset=False, **kwargs)
+    num_params = env.num_params
+    reset_no = np.zeros(num_envs, int)
+    batch_no = np.zeros(num_envs, int)
+
+    def params():
+        last = fix['reset_params'].shape[1] - 1
+        return np.stack([fix['reset_params'][e, min(reset_no[e], last)] for e in range(num_envs)])
+
+    def check_batches():
+        if func:
+            return
+        idx, cnt = env.batch_indices()
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        for e in range(num_envs):
+            want = fix['batches'][e, batch_no[e]]
+            want = want[want >= 0]
+            assert cnt[e] == len(want) and np.array_equal(idx[e, :cnt[e]], want)
+
+    obs = env.reset(init_params=params()).cpu().numpy()
+    reset_no += 1
+    assert np.array_equal(obs, fix['reset_states'].astype(np.float32))
+    check_batches()
+    clipped_ok = 0
+    for t in range(fix['actions'].shape[0]):
+        obs, rew, done, info = env.step(torch.as_tensor(fix['actions'][t], device=env.device))
+        done_np = done.cpu().numpy().astype(bool)
+        obs_np = obs.cpu().numpy().copy()
+        rew_np = rew.cpu().numpy().copy()
+        if done_np.any():
+            obs_np = env.reset(env_mask=done_np, init_params=params()).cpu().numpy()
+        reset_no += done_np
+        batch_no += 1 + done_np
+        check_batches()
+        assert np.array_equal(np.repeat(done_np, num_params), fix['dones'][t]), t
+        want = fix['states'][t]
+        err = np.abs(obs_np - want) / np.maximum(1.0, np.abs(want + 1))
+        assert np.mean(err <= 1e-4) > 0.97, (t, float(np.mean(err <= 1e-4)))
+        np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], rtol=1e-4, atol=1e-4)
+        clipped_ok += 1
+    assert clipped_ok == fix['actions'].shape[0]
+    env.close()
+
+
+def test_internal_index_stream_bit_exact_over_epochs():
+    BatchedOptEnv, _ = _mods()
+    spec = orc.ProblemSpec('softmax', 4, (), 3)
+    num_rows, batch, num_envs = 50, 16, 5
+    feats, targs = make_data(spec, num_rows)
+    perms = np.stack([orc.env_permutation(num_rows, 10 + s) for s in range(num_envs)])
+    init_orders = np.stack([np.random.RandomState(s).permutation(num_rows) for s in range(num_envs)])
+    env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch, max_batches=9,
+                        perms=perms, init_orders=init_orders, auto_reset=True)
+    stream = orc.IndexStream(num_rows, batch, perms, init_orders)
+    everyone = np.ones(num_envs, bool)
+    env.reset()
+    stream.reset(everyone)
+    rng = np.random.RandomState(3)
+    for t in range(40):
+        idx, cnt = env.batch_indices()
+        want_idx, want_cnt = stream.current()
+        assert np.array_equal(cnt.cpu().numpy(), want_cnt), t
+        assert np.array_equal(idx.cpu().numpy(), want_idx), t
+        actions = torch.as_tensor(rng.uniform(0, 2, env.num_rows).astype(np.float32), device=env.device)
+        _, _, done, _ = env.step(actions)
+        stream.advance(everyone)
+        done = done.cpu().numpy().astype(bool)
+        assert done.all() == ((t + 1) % 9 == 0)
+        if done.any():
+            stream.reset(done)
+    env.close()
+
+
+def test_full_size_properties_mlp():
+    """BASELINE config 4 shapes (784->64->10, B=32, H=5) at a reduced env count: properties
+    that do not need the oracle: determinism, row-order consistency, reset observation,
+    obs = clip(ratio)-1 of the device's own state, auto-reset at max_batches."""
+    BatchedOptEnv, ProblemSpec = _mods()
+    spec = ProblemSpec('softmax', 784, (64,), 10)
+    rng = np.random.RandomState(0)
+    num_rows, num_envs = 4096, 16
+    feats = rng.uniform(size=(num_rows, 784)).astype(np.float32)
+    labels = rng.randint(0, 10, num_rows).astype(np.int32)
+    perm = orc.lexicographic_rows(spec.size)
+    outs = []
+    for order in ('lexicographic', 'natural', 'lexicographic'):
+        env = BatchedOptEnv(spec, feats, labels, num_envs, max_batches=4, row_order=order, init_seed=5)
+        obs = env.reset()
+        assert torch.all(obs == -1.0)
+        rec = []
+        arng = np.random.RandomState(1)
+        for t in range(5):
+            nat = arng.uniform(0, 3, size=(num_envs, spec.size)).astype(np.float32)
+            rows = nat[:, perm] if order == 'lexicographic' else nat
+            obs, rew, done, info = env.step(torch.as_tensor(rows.reshape(-1), device=env.device))
+            o = obs.cpu().numpy().reshape(num_envs, spec.size, -1)
+            if order == 'lexicographic':
+                nat_o = np.empty_like(o)
+                nat_o[:, perm] = o
+                o = nat_o
+            rec.append((o, rew.cpu().numpy().copy(), done.cpu().numpy().copy(), info.cpu().numpy().copy()))
+            if t == 3:
+                assert done.all() and np.all(o == -1.0)        # auto-reset: reset observation
+            else:
+                assert not done.any()
+                assert np.all(o <= 99.0) and np.all(o >= -101.0)
+                ring = env.get_state('adj_weights').cpu().numpy()[:, 0]      # newest
+                assert np.array_equal(np.clip(ring, -100, 100).astype(np.float32) - 1, o[:, :, 0])
+        outs.append(rec)
+        env.close()
+    for a, b in zip(outs[0], outs[2]):                 # run-to-run determinism, bit exact
+        assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
+    for a, b in zip(outs[0], outs[1]):                 # row order only permutes rows
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
