@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched optimise-env step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N ...          # the reference algorithm on host CPUs
+
+Workload (N=1): BASELINE.json configs[3], the configuration the headline target is quoted
+on: MultiOptLRs, 2-layer MLP 784->64->10 on synthetic MNIST-shaped data (60000 rows),
+minibatch 32, max_history 5, 4096 lock-step envs per GPU (weak scaling: 4096 x N envs).
+One "step" = one batched env step = one launch of the fused kernel over all envs.
+
+Reported on one JSON line:
+  value     env-steps/s with actions already in HBM (device API, CUDA events, max over ranks)
+  e2e       the same metric through the reference-facing OptVecEnv.step() with HOST numpy
+            buffers: H2D of the actions and D2H of observations/rewards/dones/infos inside
+            the timed region
+  roofline  algorithmic bytes per launch (4*[P*(5H+3)+B*(D+1)] per env-step)
+            / average launch duration, against the measured HBM copy bandwidth
+  cpu_baseline  the oracle (numpy restatement of the reference) on the host cores, on a
+            bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, HID, C, BATCH, ROWS, HIST = 784, 64, 10, 32, 60000, 5
+NUM_PARAMS = D * HID + HID + HID * C + C
+BYTES_PER_ENV_STEP = 4 * (NUM_PARAMS * (5 * HIST + 3) + BATCH * (D + 1))      # 5 800 160
+WORKLOAD = 'MultiOptLRs MLP 784-64-10, B=32, H=5, 60000x784 synthetic rows'
+
+
+def synthetic_data(rows=ROWS):
+    rng = np.random.RandomState(0)
+    feats = rng.uniform(size=(rows, D)).astype(np.float32)
+    lo, hi = feats.min(0), feats.max(0)
+    feats = ((feats - lo) / (hi - lo + 1e-8)).astype(np.float32)      # utils_math.normalize
+    labels = rng.randint(0, C, size=rows).astype(np.int32)
+    return feats, labels
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the step kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh).get('dram_bytes_per_launch')
+    return None
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------- CPU (oracle) arm
+def cpu_env_steps_per_s(envs_per_thread, threads, steps, warmup):
+    """The oracle's vectorised numpy path (float32 problem arithmetic, the reference's
+    float64 env arithmetic), one oracle instance per host thread."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import optenv_oracle as orc
+    feats, labels = synthetic_data(4096)
+    spec = orc.ProblemSpec('softmax', D, (HID,), C)
+    perm = orc.env_permutation(len(feats), 0)
+
+    def make(i):
+        env = orc.BatchedOptEnvOracle(spec, feats, labels, envs_per_thread, batch_size=BATCH,
+                                      config=orc.EnvConfig.multioptlrs(400, HIST),
+                                      perms=np.tile(perm, (envs_per_thread, 1)),
+                                      compute_dtype=np.float32, init_seed=i)
+        vec = orc.OptVecEnvOracle(env)
+        vec.reset()
+        rng = np.random.RandomState(2 + i)
+        acts = rng.uniform(0, 3, size=vec.num_envs).astype(np.float32)
+        return vec, acts
+
+    workers = [make(i) for i in range(threads)]
+
+    def run(worker, count):
+        vec, acts = worker
+        for _ in range(count):
+            vec.step(acts)
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(lambda w: run(w, warmup), workers))
+        t0 = time.perf_counter()
+        list(pool.map(lambda w: run(w, steps), workers))
+        elapsed = time.perf_counter() - t0
+    return envs_per_thread * threads * steps / elapsed, elapsed
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    envs_per_thread = 2
+    value, elapsed = cpu_env_steps_per_s(envs_per_thread, threads, args.steps, args.warmup)
+    sample = '%d envs (%d threads x %d) x %d steps of the workload, oracle numpy float32' % (
+        envs_per_thread * threads, threads, envs_per_thread, args.steps)
+    line = {
+        'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * elapsed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'envs_per_step': envs_per_thread * threads,
+                   'note': 'reference algorithm (oracle port) on host CPU; TensorFlow/gym '
+                           'are not installable so the reference itself cannot run'},
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec, env_permutations
+    from custom_envs_b200.vectorize.optvecenv import DeviceOptVecEnv
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    envs = args.envs
+    feats, labels = synthetic_data()
+    # envs shard by index: rank r owns envs [r*envs, (r+1)*envs); seeds follow the global index
+    seeds = range(rank * envs, (rank + 1) * envs)
+    perms = env_permutations(ROWS, list(seeds))
+    env = BatchedOptEnv(ProblemSpec('softmax', D, (HID,), C), feats, labels, envs,
+                        batch_size=BATCH, max_batches=400, max_history=HIST,
+                        row_order=args.row_order, perms=perms, device=device,
+                        init_seed=1234 + rank)
+    del perms
+    env.reset()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(2 + rank)
+    actions = [torch.rand(env.num_rows, device=device, generator=gen) * 3.0 for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        env.step(actions[i & 1])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = env.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done_total = 0
+    start.record()
+    for i in range(args.steps):
+        env.step(actions[i & 1])
+    stop.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launch_count - launches0
+    ms = start.elapsed_time(stop)
+    done_total = int(env.done.sum().item())
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = envs * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the reference-facing VecEnv call with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    vec = DeviceOptVecEnv(env)
+    host_actions = np.random.RandomState(3 + rank).uniform(0, 3, size=(env.num_rows, 1)).astype(np.float32)
+    vec.step(host_actions)                                   # warm the pinned buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        states, rewards, dones, infos = vec.step(host_actions)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = envs * world * e2e_steps / e2e_s
+    h2d = host_actions.nbytes
+    d2h = states.nbytes + env.reward.numel() * 4 + env.done.numel() + env.info.numel() * 8
+
+    # NCCL is used only for statistics: all-gather the per-env episode reward of the last step
+    if world > 1:
+        gathered = [torch.empty_like(env.reward) for _ in range(world)]
+        dist.all_gather(gathered, env.reward)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        launch_ms = ms / args.steps
+        achieved = BYTES_PER_ENV_STEP * envs / (launch_ms * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        threads = min(cores, 32)
+        cpu_value, cpu_elapsed = cpu_env_steps_per_s(2, threads, 3, 1)
+        line = {
+            'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'envs_per_gpu': envs, 'envs_total': envs * world,
+                       'agent_rows_total': envs * world * NUM_PARAMS, 'row_order': args.row_order,
+                       'actions': 'U[0,3) float32, resident in HBM',
+                       'l2': 'per-step working set %.1f GB >> 126 MB L2 (no flush needed)'
+                             % (BYTES_PER_ENV_STEP * envs / 1e9),
+                       'envs_done_last_step': done_total, 'parallelism': 'env-index shards, dp%d' % world},
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
+                    'api': 'DeviceOptVecEnv.step(numpy actions) -> numpy states/rewards/dones + infos'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
+                         'kernel': 'optenv_kernel (1 launch per step)',
+                         'bytes_per_launch': BYTES_PER_ENV_STEP * envs},
+            'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d envs x 3 steps of the workload (oracle numpy float32, '
+                                       '%d threads), %.1f s' % (2 * threads, threads, cpu_elapsed)},
+        }
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=20)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    parser.add_argument('--envs', type=int, default=4096, help='envs per GPU')
+    parser.add_argument('--row-order', default='lexicographic', choices=['lexicographic', 'natural'])
+    parser.add_argument('--e2e-steps', type=int, default=3)
+    args = parser.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+        return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+               '--nproc-per-node', str(args.gpus), '--master-addr', '127.0.0.1',
+               '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

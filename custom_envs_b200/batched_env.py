@@ -249,6 +249,13 @@ class BatchedOptEnv:
         self._check(self.lib.b2e_get_batch_indices(self.handle, _ptr(idx), _ptr(cnt), self._stream()))
         return idx, cnt
 
+    def next_batch(self, env_mask=None):
+        """BaseProblem.next for the masked envs."""
+        mask = None
+        if env_mask is not None:
+            mask = torch.as_tensor(env_mask).to(self.device, torch.uint8).contiguous()
+        self._check(self.lib.b2e_next_batch(self.handle, _ptr(mask), self._stream()))
+
     def info_dict(self, info=None):
         """info [E,16] -> {key: np.ndarray[E]} with the reference's key names."""
         arr = (self.info if info is None else info).cpu().numpy()

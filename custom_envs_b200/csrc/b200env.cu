@@ -1019,6 +1019,21 @@ __global__ void batch_indices_kernel(Dev d, int *idx_out, int *cnt_out) {
     if (threadIdx.x == 0) cnt_out[e] = cnt;
 }
 
+// BaseProblem.next() for the masked envs (problems/optimize_nn.py:102-112)
+__global__ void next_batch_kernel(Dev d, const unsigned char *mask) {
+    const int e = blockIdx.x;
+    if (mask && !mask[e]) return;
+    EnvScalars *sc = d.sc + e;
+    __shared__ int wrap;
+    if (threadIdx.x == 0) {
+        const int cur = sc->cursor + 1;
+        wrap = cur * d.B >= d.N;
+        sc->cursor = wrap ? 0 : cur;
+    }
+    __syncthreads();
+    if (wrap) shuffle_order(d, e, sc);
+}
+
 __global__ void init_scalars_kernel(Dev d) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= d.E) return;
@@ -1417,6 +1432,15 @@ int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void
     if (!idx_out || !cnt_out) return fail(h, "b2e_get_batch_indices: null pointer");
     if (!h->ord || !h->stream_bound) return fail(h, "b2e_get_batch_indices: no internal index stream");
     batch_indices_kernel<<<h->d.E, 64, 0, (cudaStream_t)stream>>>(h->d, idx_out, cnt_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int b2e_next_batch(b2e_handle h, const uint8_t *env_mask, void *stream) {
+    if (!h) return 1;
+    if (!h->ord || !h->stream_bound) return fail(h, "b2e_next_batch: no internal index stream");
+    next_batch_kernel<<<h->d.E, 256, 0, (cudaStream_t)stream>>>(h->d, env_mask);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;

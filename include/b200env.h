@@ -136,6 +136,10 @@ int b2e_set_state(b2e_handle h, int which, const void *src, size_t bytes, void *
 /* The minibatch every env will use in its next step: idx int32 [E,B], cnt int32 [E]. */
 int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void *stream);
 
+/* BaseProblem.next (problems/optimize_nn.py:102-112) for the envs in env_mask (uint8 [E] or
+ * NULL = all): advance to the next minibatch, reshuffling at the end of an epoch. */
+int b2e_next_batch(b2e_handle h, const uint8_t *env_mask, void *stream);
+
 /* Kernel launches issued on behalf of this handle so far (bench bookkeeping). */
 int64_t b2e_launch_count(b2e_handle h);
 

@@ -1,0 +1,155 @@
+"""GPU tests of the drop-in surface: the reference's env / problem / VecEnv tests
+(tests/envs/test_env.py, tests/problems/test_base_problem.py, tests/vectorize/test_optvecenv.py)
+re-expressed against the device-backed classes, reached through the ``custom_envs`` alias."""
+import os
+import tempfile
+from functools import partial
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import optenv_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_env_step_and_reset_types():
+    from custom_envs.envs import SINGLE_AGENT_ENVIRONMENTS
+    for env_cls in SINGLE_AGENT_ENVIRONMENTS:
+        env = env_cls()                                   # default problem: Rosenbrock
+        state = env.reset()
+        assert env.current_step == 0 and env.observation_space.contains(state)
+        action = env.action_space.sample()
+        for i in range(1, 10):
+            state, reward, terminal, info = env.step(action)
+            assert env.current_step == i
+            assert env.observation_space.contains(state)
+            assert isinstance(reward, float) and isinstance(terminal, bool) and isinstance(info, dict)
+            assert info['episode'] == {'r': reward, 'l': i}
+            if terminal:
+                break
+        env.close()
+
+
+def test_multioptlrs_nn_on_iris_matches_oracle():
+    from custom_envs.envs import MultiOptLRs
+    from custom_envs import load_data
+    data = load_data('iris', 32)
+    env = MultiOptLRs(problem='nn', max_batches=8, max_history=5,
+                      problem_kwargs=dict(layers=(), data_set=data))
+    env.seed(3)
+    state = env.reset()
+    assert len(state) == 15 and all(np.all(v == -1) for v in state.values())
+    spec = orc.ProblemSpec('softmax', 4, (), 3)
+    perm = np.arange(150)
+    rs = np.random.RandomState()
+    rs.set_state(env.random_generator.get_state())
+    rs.shuffle(perm)
+    ref = orc.BatchedOptEnvOracle(spec, data.features.astype(np.float32), data.targets.argmax(1), 1,
+                                  batch_size=32, config=orc.EnvConfig.multioptlrs(8, 5), perms=perm[None])
+    ref.reset(init_params=env.model.get_parameters()[None].astype(np.float32))
+    rng = np.random.RandomState(0)
+    for t in range(8):
+        nat = rng.uniform(0, 3, size=15).astype(np.float32)
+        action = {'parameter-%d' % i: np.array([nat[i]], np.float32) for i in range(15)}
+        state, reward, terminal, info = env.step(action)
+        want_obs, want_rew, want_done, want_info = ref.step(nat[None])
+        got = np.stack([state['parameter-%d' % i] for i in range(15)])
+        err = np.abs(got - want_obs[0]) / np.maximum(1, np.abs(want_obs[0] + 1))
+        assert err.max() < 2e-4, (t, err.max())
+        assert abs(reward - want_rew[0]) < 1e-4 and terminal == bool(want_done[0])
+        assert (info['loss'] is None) == (not terminal)
+        assert abs(info['batch_loss'] - want_info['batch_loss'][0]) < 1e-5
+    assert terminal
+    env.close()
+
+
+@pytest.mark.parametrize('name', ['func', 'nn'])
+def test_base_problem_contract(name):
+    from custom_envs.problems import get_problem
+    kwargs = {} if name == 'func' else dict(layers=(8,))
+    problem = get_problem(name, **kwargs)
+    old = np.random.rand(problem.size)
+    problem.set_parameters(old)
+    assert np.allclose(problem.get_parameters(), old, atol=1e-6)        # set -> get round trip
+    gradient, loss, params = problem.get()
+    assert np.array(gradient).ndim == 1 and np.array(params).ndim == 1 and float(loss) == float(loss)
+    assert np.allclose(gradient, problem.get_gradient()) and np.isclose(loss, problem.get_loss())
+    assert np.allclose(params, problem.parameters)
+    problem.reset()
+    assert not np.allclose(problem.get_parameters(), old)
+    if name == 'nn':
+        before = problem.get_loss()
+        problem.next()
+        assert problem.get_loss() != before                             # next minibatch
+        with pytest.raises(NotImplementedError):
+            get_problem('nn')                                           # (256, 256): not built
+    with pytest.raises(RuntimeError):
+        get_problem('other')
+
+
+def test_optvecenv_fuses_monitored_envs():
+    from custom_envs.vectorize import OptVecEnv
+    from custom_envs.utils.utils_logging import Monitor
+    from custom_envs_b200.compat import make
+    from custom_envs import load_data
+    data = load_data('iris', 32)
+    keys = ('loss', 'actions_mean', 'weights_mean', 'actions_std', 'states_mean', 'grads_mean')
+    with tempfile.TemporaryDirectory() as tmp:
+        fns = [partial(Monitor, partial(make, 'MultiOptLRs-v0', problem='nn', max_batches=5,
+                                        problem_kwargs=dict(layers=(), data_set=data)),
+                       os.path.join(tmp, 'env%d' % i), info_keywords=keys) for i in range(3)]
+        seen = []
+        vec = OptVecEnv(fns, callbacks=(lambda s, r, t, i: seen.append(len(s)),))
+        assert vec.is_device_backed and vec.num_envs == 45 and vec.agent_no_list == [15, 15, 15]
+        states = vec.reset()
+        assert states.shape == (45, 15) and np.all(states == -1)
+        for t in range(11):
+            actions = np.random.RandomState(t).uniform(0, 2, size=(45, 1)).astype(np.float32)
+            states, rewards, terminals, infos = vec.step(actions)
+            assert states.shape == (45, 15) and rewards.shape == (45,) and terminals.shape == (45,)
+            assert len(infos) == 45 and infos[0] is infos[14] and infos[15] is not infos[0]
+            assert np.all(rewards[:15] == rewards[0])
+            if (t + 1) % 5 == 0:
+                assert terminals.all() and np.all(states == -1)          # auto-reset observation
+                assert infos[0]['loss'] is not None and infos[0]['episode']['l'] == 5
+            else:
+                assert not terminals.any() and infos[0]['loss'] is None
+                assert infos[0]['episode']['l'] == (t % 5) + 1
+        assert len(seen) == 11
+        episode_rewards = vec.env_method('get_episode_rewards')
+        assert [len(r) for r in episode_rewards] == [2, 2, 2]
+        assert vec.get_attr('current_step') == [1, 1, 1]
+        vec.close()
+        frame = pd.read_csv(os.path.join(tmp, 'env0.mon.csv'))
+        assert len(frame) == 2 and set(keys) <= set(frame.columns) and list(frame['l']) == [5, 5]
+
+
+def test_device_optvecenv_matches_vecenv_oracle():
+    """Host-buffer VecEnv path (lexicographic rows, auto-reset, internal stream) vs the oracle."""
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    from custom_envs_b200.vectorize import DeviceOptVecEnv
+    spec = orc.ProblemSpec('softmax', 6, (5,), 3)
+    rng = np.random.RandomState(4)
+    feats = rng.uniform(size=(50, 6)).astype(np.float32)
+    labels = rng.randint(0, 3, 50).astype(np.int32)
+    num_envs = 3
+    perms = np.stack([orc.env_permutation(50, s) for s in range(num_envs)])
+    env = BatchedOptEnv(ProblemSpec('softmax', 6, (5,), 3), feats, labels, num_envs, batch_size=16,
+                        max_batches=6, perms=perms, auto_reset=False)
+    ref = orc.OptVecEnvOracle(orc.BatchedOptEnvOracle(spec, feats, labels, num_envs, batch_size=16,
+                                                      config=orc.EnvConfig.multioptlrs(6, 5), perms=perms))
+    vec = DeviceOptVecEnv(env)
+    init = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
+    env.reset(init_params=init)
+    ref.reset(init_params=init)
+    for t in range(5):
+        actions = rng.uniform(0, 2.5, size=(vec.num_envs, 1)).astype(np.float32)
+        states, rewards, terminals, infos = vec.step(actions)
+        want_s, want_r, want_t, want_i = ref.step(actions[:, 0])
+        err = np.abs(states - want_s) / np.maximum(1, np.abs(want_s + 1))
+        assert np.mean(err < 1e-4) > 0.97
+        assert np.allclose(rewards, want_r, rtol=1e-4, atol=1e-4) and np.array_equal(terminals, want_t)
+        assert abs(infos[0]['batch_loss'] - want_i['batch_loss'][0]) < 1e-4
+    vec.close()

@@ -188,9 +188,22 @@ def test_step_parity_from_identical_states(name, row_order):
                 np.testing.assert_allclose(got[key][finite], want[finite], rtol=1e-4, err_msg=str(tag + (key,)))
                 continue
             scale = {'grads_sum': gabs, 'grads_mean': gabs / (5 * num_params)}.get(key, 1e-30)
-            err = rel_err(got[key], want, scale)
+            with np.errstate(all='ignore'):
+                err = rel_err(got[key], want, scale)
             err = np.where(np.isnan(want) & np.isnan(got[key]), 0.0, err)
-            tol = 1e-4 if key in ('actions_std', 'adjusted_grad') else RTOL
+            if key == 'adjusted_grad':
+                # x/0 -> +-inf -> nan_to_num: float64 max in the reference, float32 max on
+                # the device; a mean containing one is outside the parity domain
+                err = np.where(np.abs(want) > 1e30, 0.0, err)
+            tol = 1e-4 if key == 'actions_std' else RTOL
+            if key == 'adjusted_grad':
+                # mean_i |g_i/|gprev_i||: each term carries (error of g_i)/|gprev_i|, and the
+                # error of g_i is ~1e-6 * sum|terms| <= 10 * RTOL * mean|g|; the mean inherits the
+                # heavy tail of the ratios
+                gscale = np.abs(new_g).mean(axis=1, keepdims=True)
+                with np.errstate(all='ignore'):
+                    bound = np.mean(np.minimum(10 * RTOL * gscale / np.abs(prev_g), 200.0), axis=1)
+                err = np.where(np.abs(got[key] - want) <= bound + RTOL * np.abs(want), 0.0, err)
             assert np.all(err <= tol), (tag, key, got[key], want)
         assert np.array_equal(got['episode_l'], ref.current_step), tag
         # keep both sides on IDENTICAL states for the next step
