@@ -32,7 +32,7 @@ constexpr int MAXI = 4;           // forward work items per warp
 constexpr int NSTAT = 8;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_EVAL = 2 };
-enum { PASS_U = 0, PASS_G = 1, PASS_R = 2, PASS_E = 3 };
+enum { PASS_U = 0, PASS_G = 1, PASS_R = 2, PASS_E = 3, PASS_S = 4 };
 enum { ST_ABSW = 0, ST_LR = 1, ST_LR2 = 2, ST_G = 3, ST_ABSADJG = 4, ST_GDIFF = 5, ST_STATE = 6 };
 
 struct EnvScalars {
@@ -57,7 +57,8 @@ struct Dev {
     const float *X;
     const int *labels;
     const float *targets;
-    float *w, *gprev, *ringw, *ringg;
+    float *w, *gprev, *gnext, *ringw, *ringg;
+    double *part;
     EnvScalars *sc;
     int *ord;
     const int *perm;
@@ -66,6 +67,7 @@ struct Dev {
     int off_T, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
         off_y, off_lb, off_misc;
     int stage_stride, xslack;
+    int split, nseg;
 };
 
 struct StepArgs {
@@ -81,10 +83,12 @@ struct StepArgs {
     float *grad_out;
     float *loss_out;
     int mode;
+    int e_begin, e_count;
 };
 
 struct Stats {
-    double v[NSTAT];
+    float f[NSTAT];
+    double lr, lr2;
 };
 
 // ------------------------------------------------------------------ small helpers
@@ -124,11 +128,23 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+struct Totals {
+    double v[NSTAT];
+};
+
+__device__ __forceinline__ void zero_stats(Stats &st) {
+#pragma unroll
+    for (int i = 0; i < NSTAT; ++i) st.f[i] = 0.f;
+    st.lr = st.lr2 = 0.0;
+}
+
 // deterministic block reduction of the per-thread statistics; result valid in thread 0
-__device__ void block_reduce(Stats &st, double *red) {
+__device__ void block_reduce(const Stats &st, Totals &tot, double *red) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
     for (int i = 0; i < NSTAT; ++i) {
-        double v = warp_sum(st.v[i]);
+        double v = (i == ST_LR) ? st.lr : (i == ST_LR2) ? st.lr2 : (double)st.f[i];
+        v = warp_sum(v);
         if (lane == 0) red[warp * NSTAT + i] = v;
     }
     __syncthreads();
@@ -136,7 +152,7 @@ __device__ void block_reduce(Stats &st, double *red) {
         for (int i = 0; i < NSTAT; ++i) {
             double v = 0.0;
             for (int w = 0; w < nw; ++w) v += red[w * NSTAT + i];
-            st.v[i] = v;
+            tot.v[i] = v;
         }
     }
     __syncthreads();
@@ -451,37 +467,70 @@ struct EpiCtx {
     int e;
     int head_new, nvalid_new;
     float *wE, *gE, *rwE, *rgE;      // this env's slices
+    const float *gnewE;              // split path: g_t in HBM (written by the compute kernel)
     const float *obsL;               // [H] clipped adjusted-loss columns
 };
 
-// Warp writes the staged observation rows of its 128-parameter chunk.
+constexpr int SPAN_CAP = 160;        // rows a warp's 128-parameter chunk may span when staged by row
+
+__device__ __forceinline__ float ratio_nn(float num, float den) {    // nan_to_num(num / |den|)
+    return nan_to_num_f(__fdividef(num, fabsf(den)));
+}
+__device__ __forceinline__ float clip_only_m1(float x) {             // x already nan_to_num'ed
+    return fminf(fmaxf(x, -100.0f), 100.0f) - 1.0f;
+}
+__device__ __forceinline__ int div_small(int n, float inv) {         // exact n / OD for n < 2^15
+    return (int)(((float)n + 0.5f) * inv);
+}
+
+// Warp writes the observation rows staged for its chunk.
+//  dense: rows staged at (row - rlo) * OD (+ phase shift); holes flagged in valid_s; 16-byte
+//         stores wherever the four words belong to valid rows;
+//  else : rows staged in natural slot order, scattered word by word.
 __device__ __forceinline__ void emit_obs(const Dev &d, const StepArgs &a, const EpiCtx &cx,
-                                         const float *st, const int *rows_s, int pw0,
-                                         int lo, int hi, int soff) {
+                                         const float *st, const int *rows_s, const int *valid_s,
+                                         bool dense, int rlo, int rhi, int soff) {
     const int lane = threadIdx.x & 31;
     const int OD = d.OD;
-    if (hi <= lo) return;
-    if (!d.row_lex) {
-        const size_t gb = ((size_t)cx.e * d.P + pw0) * OD;
-        const size_t g_lo = gb + (size_t)(lo - pw0) * OD, g_hi = gb + (size_t)(hi - pw0) * OD;
-        size_t b_lo = (g_lo + 3) & ~(size_t)3, b_hi = g_hi & ~(size_t)3;
-        if (b_lo >= b_hi) { b_lo = g_hi; b_hi = g_hi; }
-        for (size_t x = g_lo + lane; x < b_lo; x += 32) a.obs[x] = st[x - gb + soff];
-        for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128)
-            *reinterpret_cast<float4 *>(a.obs + x) =
-                *reinterpret_cast<const float4 *>(st + (x - gb + soff));
-        for (size_t x = b_hi + lane; x < g_hi; x += 32) a.obs[x] = st[x - gb + soff];
+    if (rhi < rlo) return;
+    if (dense) {
+        const int span_words = (rhi - rlo + 1) * OD;
+        const size_t g_lo = ((size_t)cx.e * d.P + rlo) * OD;
+        const size_t x0 = g_lo - soff;                       // multiple of 4
+        const float inv = 1.0f / (float)OD;
+        for (int u = lane * 4; u < span_words + soff; u += 128) {
+            const int w0 = u - soff;                         // first word of this unit in the span
+            const int wa = w0 > 0 ? w0 : 0;
+            const int wb = w0 + 3 < span_words ? w0 + 3 : span_words - 1;
+            const int ra = div_small(wa, inv), rb = div_small(wb, inv);
+            const int va = valid_s[ra], vb = valid_s[rb];
+            if (w0 >= 0 && w0 + 3 < span_words && va && vb) {
+                *reinterpret_cast<float4 *>(a.obs + x0 + u) = *reinterpret_cast<const float4 *>(st + u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int w = w0 + j;
+                    if (w >= 0 && w < span_words) {
+                        const int ok = (w < rb * OD) ? va : vb;
+                        if (ok) a.obs[x0 + u + j] = st[u + j];
+                    }
+                }
+            }
+        }
     } else {
-        const int w_lo = (lo - pw0) * OD, w_hi = (hi - pw0) * OD;
         float *base = a.obs + (size_t)cx.e * d.P * OD;
-        for (int wd = w_lo + lane; wd < w_hi; wd += 32) {
-            const int pl = wd / OD, col = wd - pl * OD;
-            base[(size_t)rows_s[pl] * OD + col] = st[soff + wd];
+        const int q32 = 32 / OD, r32 = 32 - q32 * OD;
+        int pl = lane / OD, col = lane - pl * OD;
+        for (int wd = lane; wd < 128 * OD; wd += 32) {
+            const int row = rows_s[pl];
+            if (row >= 0) base[(size_t)row * OD + col] = st[wd];
+            pl += q32; col += r32;
+            if (col >= OD) { col -= OD; ++pl; }
         }
     }
 }
 
-template <int PASS>
+template <int PASS, int HT>
 __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCtx &cx,
                          int p_begin, int p_end, float *gsrc, bool tile_mode, int k0,
                          Stats &st) {
@@ -490,11 +539,11 @@ __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCt
     const int q0 = p_begin >> 2, q1 = (p_end + 3) >> 2;
     const int nchunks = (q1 - q0 + 31) >> 5;
     float *stage = sm + d.off_stage + warp * d.stage_stride;
-    int *rows_s = reinterpret_cast<int *>(sm + d.off_rows) + warp * 128;
-    const int H = d.H, OD = d.OD;
+    int *rows_s = reinterpret_cast<int *>(sm + d.off_rows) + warp * (128 + SPAN_CAP);
+    int *valid_s = rows_s + 128;
+    const int H = HT > 0 ? HT : d.H, OD = d.OD;
     for (int ch = warp; ch < nchunks; ch += nw) {
         const int p = (q0 + ch * 32 + lane) * 4;
-        const int pw0 = (q0 + ch * 32) * 4;
         bool in[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) in[i] = (p + i >= p_begin) && (p + i < p_end);
@@ -515,30 +564,37 @@ __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCt
         int rows[4] = {p, p + 1, p + 2, p + 3};
         float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (any) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (in[i]) g[i] = gsrc[gi[i]];
             if (d.row_lex && (PASS == PASS_U || PASS == PASS_G)) {
                 const int4 r4 = *reinterpret_cast<const int4 *>(d.row_of_param + p);
                 rows[0] = r4.x; rows[1] = r4.y; rows[2] = r4.z; rows[3] = r4.w;
+            }
+            if (PASS == PASS_G && cx.gnewE) {
+                const float4 g4 = *reinterpret_cast<const float4 *>(cx.gnewE + p);
+                g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (in[i]) g[i] = gsrc[gi[i]];
             }
         }
         if (PASS == PASS_U) {
             if (any) {
                 const float4 w4 = *reinterpret_cast<const float4 *>(cx.wE + p);
+                const float *act = a.actions + (size_t)cx.e * d.P;
+                float av[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = in[i] ? act[rows[i]] : 0.f;
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
                 float wn[4], aw[4];
-                const float *act = a.actions + (size_t)cx.e * d.P;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float av = in[i] ? act[rows[i]] : 0.f;
-                    const float lr = action_to_lr(av, d.act_ver);
+                    const float lr = action_to_lr(av[i], d.act_ver);
                     wn[i] = fmaf(-g[i], lr, wv[i]);                 // multioptlrs.py:87
-                    aw[i] = nan_to_num_f(wn[i] / fabsf(wv[i]));     // utils_env.py:158-159
+                    aw[i] = ratio_nn(wn[i], wv[i]);                 // utils_env.py:158-159
                     if (in[i]) {
-                        st.v[ST_ABSW] += (double)fabsf(wn[i]);
-                        st.v[ST_LR] += (double)lr;
-                        st.v[ST_LR2] += (double)lr * (double)lr;
+                        st.f[ST_ABSW] += fabsf(wn[i]);
+                        st.lr += (double)lr;
+                        st.lr2 += (double)lr * (double)lr;
                         gsrc[gi[i]] = wn[i];
                     }
                 }
@@ -552,70 +608,142 @@ __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCt
                         if (in[i]) { cx.wE[p + i] = wn[i]; rw[i] = aw[i]; }
                 }
             }
-        } else if (PASS == PASS_R || PASS == PASS_E) {
+        } else if (PASS == PASS_R || PASS == PASS_E || PASS == PASS_S) {
             if (any) {
-                float *dst = (PASS == PASS_R) ? cx.gE + p : a.grad_out + (size_t)cx.e * d.P + p;
+                float *dst = (PASS == PASS_R) ? cx.gE + p
+                           : (PASS == PASS_S) ? d.gnext + (size_t)cx.e * d.Pp + p
+                                              : a.grad_out + (size_t)cx.e * d.P + p;
+                if (all && PASS != PASS_E) {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+                    st.f[ST_G] += (g[0] + g[1]) + (g[2] + g[3]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (in[i]) { dst[i] = g[i]; st.v[ST_G] += (double)g[i]; }
+                    for (int i = 0; i < 4; ++i)
+                        if (in[i]) { dst[i] = g[i]; st.f[ST_G] += g[i]; }
+                }
             }
         } else {   // PASS_G
-            // stage shift so that smem and global share their 16-byte phase
-            const int soff = d.row_lex ? 0 : (int)((((size_t)cx.e * d.P + pw0) * OD) & 3);
-            float *srow = stage + soff + (lane * 4) * OD;
+            // ---- issue every global load of this quad first
+            constexpr int HB = HT > 0 ? HT : 1;
+            float4 gp4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 rw4[HB], rg4[HB];
+            if (HT > 0) {
+#pragma unroll
+                for (int h = 0; h < HB; ++h) rw4[h] = rg4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             if (any) {
-                const float4 gp4 = *reinterpret_cast<const float4 *>(cx.gE + p);
+                gp4 = *reinterpret_cast<const float4 *>(cx.gE + p);
+                if (HT > 0) {
+#pragma unroll
+                    for (int h = 0; h < HB; ++h) {
+                        if (h < cx.nvalid_new) {
+                            int slot = cx.head_new - h;
+                            slot += slot < 0 ? HB : 0;
+                            rw4[h] = *reinterpret_cast<const float4 *>(cx.rwE + (size_t)slot * d.Pp + p);
+                            if (h > 0)
+                                rg4[h] = *reinterpret_cast<const float4 *>(cx.rgE + (size_t)slot * d.Pp + p);
+                        }
+                    }
+                }
+            }
+            // ---- row span of this warp's chunk
+            int rlo = 0x7fffffff, rhi = -1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (in[i]) { rlo = min(rlo, rows[i]); rhi = max(rhi, rows[i]); }
+            rlo = __reduce_min_sync(0xffffffffu, rlo);
+            rhi = __reduce_max_sync(0xffffffffu, rhi);
+            const bool dense = (rhi - rlo) < SPAN_CAP;
+            const int soff = dense ? (int)((((size_t)cx.e * d.P + rlo) * OD) & 3) : 0;
+            if (dense) {
+                for (int i = lane; i < SPAN_CAP; i += 32) valid_s[i] = 0;
+                __syncwarp();
+            }
+            if (any) {
                 const float gp[4] = {gp4.x, gp4.y, gp4.z, gp4.w};
                 float ag[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    ag[i] = nan_to_num_f(g[i] / fabsf(gp[i]));      // utils_env.py:156-157
+                    ag[i] = ratio_nn(g[i], gp[i]);                  // utils_env.py:156-157
                     if (in[i]) {
-                        st.v[ST_G] += (double)g[i];
-                        st.v[ST_ABSADJG] += (double)fabsf(ag[i]);
-                        st.v[ST_GDIFF] += (double)fabsf(g[i] - gp[i]);
+                        st.f[ST_G] += g[i];
+                        st.f[ST_ABSADJG] += fabsf(ag[i]);
+                        st.f[ST_GDIFF] += fabsf(g[i] - gp[i]);
                     }
                 }
                 float *rg = cx.rgE + (size_t)cx.head_new * d.Pp + p;
+                const bool keep_g = cx.gnewE == nullptr;   // split path ping-pongs the g buffers
                 if (all) {
-                    *reinterpret_cast<float4 *>(cx.gE + p) = make_float4(g[0], g[1], g[2], g[3]);
+                    if (keep_g)
+                        *reinterpret_cast<float4 *>(cx.gE + p) = make_float4(g[0], g[1], g[2], g[3]);
                     *reinterpret_cast<float4 *>(rg) = make_float4(ag[0], ag[1], ag[2], ag[3]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (in[i]) { cx.gE[p + i] = g[i]; rg[i] = ag[i]; }
+                        if (in[i]) { if (keep_g) cx.gE[p + i] = g[i]; rg[i] = ag[i]; }
                 }
                 // observation rows: [adj_w newest..oldest | adj_L | adj_g newest..oldest]
-                double sabs = 0.0;
-                for (int h = 0; h < H; ++h) {
-                    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = w4;
-                    if (h < cx.nvalid_new) {
-                        int slot = cx.head_new - h;
-                        slot += slot < 0 ? H : 0;
-                        w4 = *reinterpret_cast<const float4 *>(cx.rwE + (size_t)slot * d.Pp + p);
-                        if (h > 0)
-                            g4 = *reinterpret_cast<const float4 *>(cx.rgE + (size_t)slot * d.Pp + p);
-                        else
-                            g4 = make_float4(ag[0], ag[1], ag[2], ag[3]);
-                    }
-                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-                    const float ol = cx.obsL[h];
+                float *srow[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (in[i]) sabs += (double)fabsf(wv[i]) + (double)fabsf(gv[i]);
-                        srow[i * OD + h] = clip_m1(wv[i]);
-                        srow[i * OD + H + h] = ol;
-                        srow[i * OD + 2 * H + h] = clip_m1(gv[i]);
+                for (int i = 0; i < 4; ++i)
+                    srow[i] = stage + soff + (dense ? (in[i] ? rows[i] - rlo : 0) : lane * 4 + i) * OD;
+                float sabs = 0.f;
+                if (HT > 0) {
+#pragma unroll
+                    for (int h = 0; h < HB; ++h) {
+                        const float wv[4] = {rw4[h].x, rw4[h].y, rw4[h].z, rw4[h].w};
+                        const float gv[4] = {h ? rg4[h].x : ag[0], h ? rg4[h].y : ag[1],
+                                             h ? rg4[h].z : ag[2], h ? rg4[h].w : ag[3]};
+                        const float ol = cx.obsL[h];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (in[i]) {
+                                sabs += fabsf(wv[i]) + fabsf(gv[i]);
+                                srow[i][h] = clip_only_m1(wv[i]);
+                                srow[i][HB + h] = ol;
+                                srow[i][2 * HB + h] = clip_only_m1(gv[i]);
+                            }
+                        }
+                    }
+                } else {
+                    for (int h = 0; h < H; ++h) {
+                        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = w4;
+                        if (h < cx.nvalid_new) {
+                            int slot = cx.head_new - h;
+                            slot += slot < 0 ? H : 0;
+                            w4 = *reinterpret_cast<const float4 *>(cx.rwE + (size_t)slot * d.Pp + p);
+                            if (h > 0)
+                                g4 = *reinterpret_cast<const float4 *>(cx.rgE + (size_t)slot * d.Pp + p);
+                            else
+                                g4 = make_float4(ag[0], ag[1], ag[2], ag[3]);
+                        }
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                        const float ol = cx.obsL[h];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (in[i]) {
+                                sabs += fabsf(wv[i]) + fabsf(gv[i]);
+                                srow[i][h] = clip_only_m1(wv[i]);
+                                srow[i][H + h] = ol;
+                                srow[i][2 * H + h] = clip_only_m1(gv[i]);
+                            }
+                        }
                     }
                 }
-                st.v[ST_STATE] += sabs;
-            }
+                st.f[ST_STATE] += sabs;
+                if (dense) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rows_s[lane * 4 + i] = rows[i];
+                    for (int i = 0; i < 4; ++i)
+                        if (in[i]) valid_s[rows[i] - rlo] = 1;
+                }
+            }
+            if (!dense) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rows_s[lane * 4 + i] = in[i] ? rows[i] : -1;
+            }
             __syncwarp();
-            const int lo = max(pw0, p_begin), hi = min(pw0 + 128, p_end);
-            emit_obs(d, a, cx, stage, rows_s, pw0, lo, hi, soff);
+            emit_obs(d, a, cx, stage, rows_s, valid_s, dense, rlo, rhi, soff);
             __syncwarp();
         }
     }
@@ -665,12 +793,12 @@ __device__ float eval_current(const Dev &d, const StepArgs &a, float *sm, const 
     if (d.ntiles) forward_from_global(d, sm, cx.wE);
     const float loss = tail_eval(d, sm, cnt);
     float *T = sm + d.off_T;
-    epilogue<PASS>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+    epilogue<PASS, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
     for (int t = 0; t < d.ntiles; ++t) {
         const int k0 = t * d.KT;
         g_compute(d, sm, T, k0, cnt);
         __syncthreads();
-        epilogue<PASS>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
+        epilogue<PASS, 0>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
         __syncthreads();
     }
     return loss;
@@ -682,6 +810,7 @@ __device__ void make_ctx(const Dev &d, int e, EpiCtx &cx) {
     cx.gE = d.gprev + (size_t)e * d.Pp;
     cx.rwE = d.ringw + (size_t)e * d.H * d.Pp;
     cx.rgE = d.ringg + (size_t)e * d.H * d.Pp;
+    cx.gnewE = nullptr;
     cx.head_new = 0;
     cx.nvalid_new = 0;
     cx.obsL = nullptr;
@@ -714,15 +843,16 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     }
     __syncthreads();
     Stats st;
-    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+    zero_stats(st);
     const float loss = eval_current<PASS_R>(d, a, sm, cx, cnt, st);
-    block_reduce(st, reinterpret_cast<double *>(sm + d.off_red));
+    Totals tot;
+    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red));
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
         for (int i = 0; i < B2E_MAX_HISTORY; ++i) sc->adj_loss[i] = 0.f;
         sc->raw_pos = 0;
         sc->raw_loss[0] = loss;
-        sc->raw_gsum[0] = st.v[ST_G];
+        sc->raw_gsum[0] = tot.v[ST_G];
         sc->loss_prev = loss;
         sc->head = d.H - 1;
         sc->nvalid = 0;
@@ -737,6 +867,7 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     __syncthreads();
 }
 
+template <int HT>
 __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     EnvScalars *sc = d.sc + e;
     EpiCtx cx;
@@ -752,13 +883,13 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     cx.nvalid_new = nvalid_new;
     cx.obsL = misc + 8;
     Stats st;
-    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+    zero_stats(st);
 
     // ---- gradient at w_{t-1}, update, forward at w_t (fused per tile)
     load_tail(d, sm, cx.wE);
     if (d.ntiles) forward_from_global(d, sm, cx.wE);
     tail_eval(d, sm, cnt);
-    epilogue<PASS_U>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+    epilogue<PASS_U, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
     __syncthreads();
     {   // tail: tg now holds w_t of the tail; make it the live tail parameters
         float *tw = sm + d.off_tw, *tg = sm + d.off_tg;
@@ -771,7 +902,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         const int krows = min(d.KT, d.D - k0), krows4 = (krows + 3) & ~3;
         g_compute(d, sm, T, k0, cnt);
         __syncthreads();
-        epilogue<PASS_U>(d, a, sm, cx, k0 * d.N1, (k0 + krows) * d.N1, T, true, k0, st);
+        epilogue<PASS_U, 0>(d, a, sm, cx, k0 * d.N1, (k0 + krows) * d.N1, T, true, k0, st);
         for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
         if (d.N1p != d.N1)
             for (int i = threadIdx.x; i < krows * (d.N1p - d.N1); i += blockDim.x) {
@@ -804,15 +935,27 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         }
     }
     __syncthreads();
-    epilogue<PASS_G>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
-    for (int t = 0; t < d.ntiles; ++t) {
-        const int k0 = t * d.KT;
-        g_compute(d, sm, T, k0, cnt);
-        __syncthreads();
-        epilogue<PASS_G>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
-        __syncthreads();
+    if (d.split) {      // g_t goes to HBM; the observation kernel takes it from there
+        epilogue<PASS_S, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+        for (int t = 0; t < d.ntiles; ++t) {
+            const int k0 = t * d.KT;
+            g_compute(d, sm, T, k0, cnt);
+            __syncthreads();
+            epilogue<PASS_S, 0>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
+            __syncthreads();
+        }
+    } else {
+        epilogue<PASS_G, HT>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
+        for (int t = 0; t < d.ntiles; ++t) {
+            const int k0 = t * d.KT;
+            g_compute(d, sm, T, k0, cnt);
+            __syncthreads();
+            epilogue<PASS_G, HT>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
+            __syncthreads();
+        }
     }
-    block_reduce(st, reinterpret_cast<double *>(sm + d.off_red));
+    Totals tot;
+    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red));
 
     // ---- scalars: reward, done, info, history bookkeeping (thread 0)
     bool done = false;
@@ -839,7 +982,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
         sc->raw_pos = rp;
         sc->raw_loss[rp] = loss;
-        sc->raw_gsum[rp] = st.v[ST_G];
+        sc->raw_gsum[rp] = tot.v[ST_G];
         sc->loss_prev = loss;
         sc->adj_loss[head_new] = (float)adjl;
         sc->head = head_new;
@@ -849,15 +992,15 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         for (int i = 0; i < RAW_DEPTH; ++i) { gsum += sc->raw_gsum[i]; lsum += (double)sc->raw_loss[i]; }
         for (int h = 0; h < d.H; ++h) labs += (double)misc[8 + B2E_MAX_HISTORY + h];
         const double P = (double)d.P;
-        const double lr_mean = st.v[ST_LR] / P;
-        double lr_var = st.v[ST_LR2] / P - lr_mean * lr_mean;
+        const double lr_mean = tot.v[ST_LR] / P;
+        double lr_var = tot.v[ST_LR2] / P - lr_mean * lr_mean;
         lr_var = lr_var > 0.0 ? lr_var : 0.0;
-        const double ssum = st.v[ST_STATE] + P * labs;
+        const double ssum = tot.v[ST_STATE] + P * labs;
         double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
         info[0] = done ? L : nan("");                              // multioptlrs.py:108-110
         info[1] = L;
-        info[2] = st.v[ST_ABSW] / P;
-        info[3] = st.v[ST_ABSW];
+        info[2] = tot.v[ST_ABSW] / P;
+        info[3] = tot.v[ST_ABSW];
         info[4] = lr_mean;
         info[5] = sqrt(lr_var);
         info[6] = ssum / (P * (double)d.OD);
@@ -866,8 +1009,8 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         info[9] = gsum;
         info[10] = lsum / RAW_DEPTH;
         info[11] = adjl;
-        info[12] = st.v[ST_ABSADJG] / P;
-        info[13] = st.v[ST_GDIFF] / P;
+        info[12] = tot.v[ST_ABSADJG] / P;
+        info[13] = tot.v[ST_GDIFF] / P;
         info[14] = reward;                                         // baseenvironment.py:40
         info[15] = (double)step;
         a.reward[e] = (float)reward;
@@ -886,7 +1029,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     done = misc[1] != 0.f;
     __syncthreads();
     if (wrap) shuffle_order(d, e, sc);
-    if (done && d.auto_reset) reset_env(d, a, sm, e);
+    if (done && d.auto_reset && !d.split) reset_env(d, a, sm, e);
 }
 
 __device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
@@ -897,18 +1040,20 @@ __device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     current_batch(d, a, e, sc, idx, cnt);
     if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
     Stats st;
-    for (int i = 0; i < NSTAT; ++i) st.v[i] = 0.0;
+    zero_stats(st);
     const float loss = eval_current<PASS_E>(d, a, sm, cx, cnt, st);
     if (threadIdx.x == 0) a.loss_out[e] = loss;
     __syncthreads();
 }
 
+template <int HT>
 __global__ void __launch_bounds__(512) optenv_kernel(const __grid_constant__ Dev d,
                                                      const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
-    for (int e = blockIdx.x; e < d.E; e += gridDim.x) {
+    const int e_end = a.e_begin + a.e_count;
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
         if (a.mode == MODE_STEP) {
-            step_env(d, a, sm, e);
+            step_env<HT>(d, a, sm, e);
         } else if (a.mode == MODE_RESET) {
             if (a.mask == nullptr || a.mask[e]) reset_env(d, a, sm, e);
         } else {
@@ -916,6 +1061,86 @@ __global__ void __launch_bounds__(512) optenv_kernel(const __grid_constant__ Dev
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------- split path: observation kernel
+// Streams one segment (16 chunks of 128 parameters) of one env: reads g_t, g_{t-1} and the
+// ratio rings, appends the new gradient ratio, writes the observation rows and the
+// per-segment partial statistics.  Memory bound; runs next to the compute kernel.
+constexpr int SEG_CHUNKS = 16;
+
+template <int HT>
+__global__ void __launch_bounds__(64) obs_kernel(const __grid_constant__ Dev d,
+                                                 const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int e = a.e_begin + blockIdx.y;
+    const int seg = blockIdx.x;
+    const EnvScalars *sc = d.sc + e;
+    float *obsL = sm + d.off_misc;
+    const int head = sc->head, nvalid = sc->nvalid;       // already advanced by the compute kernel
+    if (threadIdx.x < d.H) {
+        const int h = threadIdx.x;
+        float v = 0.f;
+        if (h < nvalid) {
+            int slot = head - h;
+            slot += slot < 0 ? d.H : 0;
+            v = sc->adj_loss[slot];
+        }
+        obsL[h] = clip_m1(v);
+    }
+    __syncthreads();
+    EpiCtx cx;
+    make_ctx(d, e, cx);
+    cx.gnewE = d.gnext + (size_t)e * d.Pp;
+    cx.head_new = head;
+    cx.nvalid_new = nvalid;
+    cx.obsL = obsL;
+    Stats st;
+    zero_stats(st);
+    const int p_begin = seg * SEG_CHUNKS * 128;
+    const int p_end = min(d.P, p_begin + SEG_CHUNKS * 128);
+    epilogue<PASS_G, HT>(d, a, sm, cx, p_begin, p_end, nullptr, false, 0, st);
+    // per-segment partials (deterministic: fixed order inside the CTA, summed per env later)
+    __shared__ double red[2 * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double v0 = warp_sum((double)st.f[ST_ABSADJG]), v1 = warp_sum((double)st.f[ST_GDIFF]);
+    const double v2 = warp_sum((double)st.f[ST_STATE]);
+    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *out = d.part + ((size_t)e * d.nseg + seg) * 4;
+        const int nw = blockDim.x >> 5;
+        for (int i = 0; i < 3; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < nw; ++w) v += red[w * 4 + i];
+            out[i] = v;
+        }
+    }
+}
+
+// info entries that need the observation kernel's partial sums (states_*, adjusted_grad, grad_diff)
+__global__ void info_finalize_kernel(Dev d, StepArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= d.E) return;
+    const EnvScalars *sc = d.sc + e;
+    double absadjg = 0.0, gdiff = 0.0, state = 0.0;
+    for (int s = 0; s < d.nseg; ++s) {
+        const double *in = d.part + ((size_t)e * d.nseg + s) * 4;
+        absadjg += in[0]; gdiff += in[1]; state += in[2];
+    }
+    double labs = 0.0;
+    for (int h = 0; h < d.H && h < sc->nvalid; ++h) {
+        int slot = sc->head - h;
+        slot += slot < 0 ? d.H : 0;
+        labs += (double)fabsf(sc->adj_loss[slot]);
+    }
+    const double P = (double)d.P;
+    const double ssum = state + P * labs;
+    double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
+    info[6] = ssum / (P * (double)d.OD);
+    info[7] = ssum;
+    info[12] = absadjg / P;
+    info[13] = gdiff / P;
 }
 
 // ------------------------------------------------------------ utility kernels
@@ -1054,8 +1279,15 @@ struct b2e_env {
     size_t smem_bytes;
     float *X, *targets_f;
     int *labels, *ord, *perm, *row_of_param;
-    float *w, *gprev, *ringw, *ringg;
+    float *w, *gprev, *gnext, *ringw, *ringg;
+    double *part;
     EnvScalars *sc;
+    Dev d_obs;                       // Dev with the observation kernel's shared-memory layout
+    size_t smem_obs;
+    int chunk_envs;
+    cudaStream_t side;               // the observation kernel runs here, next to the compute kernel
+    cudaEvent_t ev_fork, ev_join;
+    cudaEvent_t ev_chunk[64];
     bool dataset_bound, stream_bound;
     int64_t launches;
     std::string error;
@@ -1167,19 +1399,34 @@ int configure(b2e_handle h) {
     const int red_floats = 2 * NSTAT * 16;
     const int fred = d.nks > 1 ? d.nks * d.B * d.N1p : 0;
     d.off_red = off; off += round_up(fred > red_floats ? fred : red_floats, 4);
-    d.stage_stride = round_up(128 * d.OD + 4, 4);
-    d.off_stage = off; off += nw * d.stage_stride;
-    d.off_rows = off; off += nw * 128;
+    // large problems: compute kernel + streaming observation kernel
+    d.split = (d.P >= 4096 && c.env_kind == B2E_ENV_MULTIOPTLRS) ? 1 : 0;
+    d.nseg = (d.P + SEG_CHUNKS * 128 - 1) / (SEG_CHUNKS * 128);
+    d.stage_stride = round_up(SPAN_CAP * d.OD + 8, 4);
+    d.off_stage = off; off += d.split ? 0 : nw * d.stage_stride;
+    d.off_rows = off; off += d.split ? 0 : nw * (128 + SPAN_CAP);
     d.off_idx = off; off += round_up(d.B, 4);
     d.off_y = off; off += round_up(d.B * (d.kind == B2E_PROBLEM_LINREG ? d.C : 1), 4);
     d.off_lb = off; off += round_up(d.B, 4);
     d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
     h->smem_bytes = (size_t)off * sizeof(float);
+    // observation kernel: 2 warps, each with its own staging
+    h->d_obs = d;
+    Dev &o = h->d_obs;
+    const int nw2 = 2;
+    o.off_stage = 0;
+    o.off_rows = nw2 * o.stage_stride;
+    o.off_misc = o.off_rows + nw2 * (128 + SPAN_CAP);
+    h->smem_obs = (size_t)(o.off_misc + B2E_MAX_HISTORY) * sizeof(float);
     return 0;
 }
 
-int launch(b2e_handle h, const StepArgs &args, void *stream) {
-    optenv_kernel<<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
+int launch(b2e_handle h, StepArgs args, void *stream) {
+    if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
+    if (h->d.H == 5)
+        optenv_kernel<5><<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
+    else
+        optenv_kernel<0><<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -1229,7 +1476,9 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->launches = 0;
     h->dataset_bound = h->stream_bound = false;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = nullptr;
-    h->w = h->gprev = h->ringw = h->ringg = nullptr; h->sc = nullptr;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr;
+    h->side = nullptr; h->ev_fork = h->ev_join = nullptr;
+    for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bail("b2e_create: cudaSetDevice failed");
     if (configure(h)) return bail(h->error);
@@ -1239,12 +1488,16 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return bail("b2e_create: problem does not fit the fused kernel's shared memory (" +
                     std::to_string(h->smem_bytes) + " bytes needed)");
-    if (cudaFuncSetAttribute(optenv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(optenv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)h->smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(optenv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)h->smem_bytes) != cudaSuccess)
         return bail("b2e_create: cudaFuncSetAttribute(smem) failed");
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel, h->nthreads,
-                                                      h->smem_bytes) != cudaSuccess || occ < 1)
+    cudaError_t occ_err = cfg->max_history == 5
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel<5>, h->nthreads, h->smem_bytes)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel<0>, h->nthreads, h->smem_bytes);
+    if (occ_err != cudaSuccess || occ < 1)
         return bail("b2e_create: kernel does not fit an SM");
     const long long resident = (long long)occ * h->num_sms;
     h->grid = (int)(cfg->num_envs < resident ? cfg->num_envs : resident);
@@ -1255,6 +1508,25 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         !dmalloc((void **)&h->ringw, EP * d.H * 4) || !dmalloc((void **)&h->ringg, EP * d.H * 4) ||
         !dmalloc((void **)&h->sc, (size_t)d.E * sizeof(EnvScalars)))
         return bail("b2e_create: cudaMalloc of env state failed");
+    if (d.split) {
+        if (!dmalloc((void **)&h->gnext, EP * 4) ||
+            !dmalloc((void **)&h->part, (size_t)d.E * d.nseg * 4 * sizeof(double)))
+            return bail("b2e_create: cudaMalloc of the split-path buffers failed");
+        cudaMemset(h->gnext, 0, EP * 4);
+        if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+            return bail("b2e_create: stream/event creation failed");
+        for (auto &ev : h->ev_chunk)
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+                return bail("b2e_create: event creation failed");
+        if (cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_obs) != cudaSuccess ||
+            cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_obs) != cudaSuccess)
+            return bail("b2e_create: observation kernel does not fit (max_history too large)");
+        h->chunk_envs = 4 * h->num_sms;
+    }
     cudaMemset(h->w, 0, EP * 4); cudaMemset(h->gprev, 0, EP * 4);
     cudaMemset(h->ringw, 0, EP * d.H * 4); cudaMemset(h->ringg, 0, EP * d.H * 4);
     if (d.kind != B2E_PROBLEM_FUNC) {
@@ -1279,8 +1551,15 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (!ok) return bail("b2e_create: row table: " + err);
     }
     d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
-    d.w = h->w; d.gprev = h->gprev; d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
+    d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part;
+    d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
     d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param;
+    {
+        Dev &o = h->d_obs;
+        o.X = d.X; o.labels = d.labels; o.targets = d.targets; o.w = d.w; o.gprev = d.gprev;
+        o.gnext = d.gnext; o.part = d.part; o.ringw = d.ringw; o.ringg = d.ringg; o.sc = d.sc;
+        o.ord = d.ord; o.perm = d.perm; o.perm_stride = d.perm_stride; o.row_of_param = d.row_of_param;
+    }
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
@@ -1291,7 +1570,11 @@ void b2e_destroy(b2e_handle h) {
     if (!h) return;
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
     cudaFree(h->row_of_param); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
-    cudaFree(h->ringg); cudaFree(h->sc);
+    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     delete h;
 }
 
@@ -1364,7 +1647,45 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     memset(&a, 0, sizeof(a));
     a.mode = MODE_STEP; a.actions = actions; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
     a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out;
-    return launch(h, a, stream);
+    if (!h->d.split) return launch(h, a, stream);
+    // ---- split path: per chunk of envs, compute kernel on the caller's stream and the
+    // streaming observation kernel on the side stream, so chunk c's observations are
+    // written while chunk c+1 is being computed
+    cudaStream_t main_s = (cudaStream_t)stream;
+    Dev &d = h->d;
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_s));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    int chunk = 0;
+    for (int e0 = 0; e0 < d.E; e0 += h->chunk_envs, ++chunk) {
+        const int ec = d.E - e0 < h->chunk_envs ? d.E - e0 : h->chunk_envs;
+        StepArgs ac = a;
+        ac.e_begin = e0; ac.e_count = ec;
+        if (launch(h, ac, main_s)) return 1;
+        cudaEvent_t ev = h->ev_chunk[chunk & 63];
+        CUDA_TRY(h, cudaEventRecord(ev, main_s));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->side, ev, 0));
+        h->d_obs.gprev = d.gprev; h->d_obs.gnext = d.gnext; h->d_obs.perm_stride = d.perm_stride;
+        const dim3 grid(d.nseg, ec);
+        if (d.H == 5) obs_kernel<5><<<grid, 64, h->smem_obs, h->side>>>(h->d_obs, ac);
+        else obs_kernel<0><<<grid, 64, h->smem_obs, h->side>>>(h->d_obs, ac);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
+    CUDA_TRY(h, cudaStreamWaitEvent(main_s, h->ev_join, 0));
+    info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    {   // g buffers ping-pong: what was g_t is now the newest raw-history gradient
+        float *t = d.gprev; d.gprev = d.gnext; d.gnext = t;
+    }
+    if (d.auto_reset) {
+        StepArgs r;
+        memset(&r, 0, sizeof(r));
+        r.mode = MODE_RESET; r.mask = done_out; r.obs = obs_out;
+        return launch(h, r, main_s);
+    }
+    return 0;
 }
 
 int b2e_eval(b2e_handle h, const int32_t *batch_idx, const int32_t *batch_cnt, float *grad_out,
@@ -1400,7 +1721,7 @@ static int state_io(b2e_handle h, int which, void *user, size_t bytes, void *str
                            std::to_string(want));
     switch (which) {
         case B2E_STATE_PARAMS: case B2E_STATE_GRAD_PREV:
-            strided_copy_kernel<<<1184, 256, 0, s>>>(which == B2E_STATE_PARAMS ? h->w : h->gprev,
+            strided_copy_kernel<<<1184, 256, 0, s>>>(which == B2E_STATE_PARAMS ? h->w : d.gprev,
                                                      (float *)user, d.E, d.P, d.Pp, to_user);
             break;
         case B2E_STATE_ADJ_WEIGHTS: case B2E_STATE_ADJ_GRADS: case B2E_STATE_ADJ_LOSSES:
