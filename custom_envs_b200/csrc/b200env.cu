@@ -64,6 +64,7 @@ struct Dev {
     const int *perm;
     long long perm_stride;
     const int *row_of_param;
+    const int *param_of_row;
     int off_T, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
         off_y, off_lb, off_misc;
     int stage_stride, xslack;
@@ -1064,55 +1065,129 @@ __global__ void __launch_bounds__(512) optenv_kernel(const __grid_constant__ Dev
 }
 
 // ------------------------------------------------- split path: observation kernel
-// Streams one segment (16 chunks of 128 parameters) of one env: reads g_t, g_{t-1} and the
-// ratio rings, appends the new gradient ratio, writes the observation rows and the
-// per-segment partial statistics.  Memory bound; runs next to the compute kernel.
-constexpr int SEG_CHUNKS = 16;
+// Row-space streaming kernel: lane = one agent row (= one parameter, through the row
+// table).  Reads g_t, g_{t-1} and the ratio rings of that parameter, appends the new
+// gradient ratio, builds the observation row in shared memory and the warp writes its 32
+// rows as one contiguous block.  Consecutive rows are (runs of) consecutive parameters in
+// lexicographic order, so the 4-byte gathers stay sector efficient.
+constexpr int OBS_WARPS = 8;
+constexpr int OBS_ITERS = 8;
+constexpr int SEG_ROWS = OBS_WARPS * OBS_ITERS * 32;
 
 template <int HT>
-__global__ void __launch_bounds__(64) obs_kernel(const __grid_constant__ Dev d,
-                                                 const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_constant__ Dev d,
+                                                             const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int e = a.e_begin + blockIdx.y;
     const int seg = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const EnvScalars *sc = d.sc + e;
-    float *obsL = sm + d.off_misc;
-    const int head = sc->head, nvalid = sc->nvalid;       // already advanced by the compute kernel
-    if (threadIdx.x < d.H) {
+    const int H = HT > 0 ? HT : d.H, OD = d.OD;
+    float *obsL = sm;                                         // [B2E_MAX_HISTORY]
+    float *stage = sm + B2E_MAX_HISTORY + warp * (32 * OD + 8);
+    const int head = sc->head, nvalid = sc->nvalid;          // already advanced by the compute kernel
+    if (threadIdx.x < H) {
         const int h = threadIdx.x;
         float v = 0.f;
         if (h < nvalid) {
             int slot = head - h;
-            slot += slot < 0 ? d.H : 0;
+            slot += slot < 0 ? H : 0;
             v = sc->adj_loss[slot];
         }
         obsL[h] = clip_m1(v);
     }
     __syncthreads();
-    EpiCtx cx;
-    make_ctx(d, e, cx);
-    cx.gnewE = d.gnext + (size_t)e * d.Pp;
-    cx.head_new = head;
-    cx.nvalid_new = nvalid;
-    cx.obsL = obsL;
-    Stats st;
-    zero_stats(st);
-    const int p_begin = seg * SEG_CHUNKS * 128;
-    const int p_end = min(d.P, p_begin + SEG_CHUNKS * 128);
-    epilogue<PASS_G, HT>(d, a, sm, cx, p_begin, p_end, nullptr, false, 0, st);
+    const float *gnew = d.gnext + (size_t)e * d.Pp;
+    const float *gold = d.gprev + (size_t)e * d.Pp;
+    const float *rw = d.ringw + (size_t)e * H * d.Pp;
+    float *rg = d.ringg + (size_t)e * H * d.Pp;
+    float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
+    for (int it = 0; it < OBS_ITERS; ++it) {
+        const int rbase = seg * SEG_ROWS + (it * OBS_WARPS + warp) * 32;
+        if (rbase >= d.P) break;
+        const int r = rbase + lane;
+        const bool ok = r < d.P;
+        const int p = ok ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+        constexpr int HB = HT > 0 ? HT : 1;
+        float wv[HB], gv[HB];
+        const float g = gnew[p], gp = gold[p];
+        if (HT > 0) {
+#pragma unroll
+            for (int h = 0; h < HB; ++h) {
+                wv[h] = 0.f; gv[h] = 0.f;
+                if (h < nvalid) {
+                    int slot = head - h;
+                    slot += slot < 0 ? HB : 0;
+                    wv[h] = rw[(size_t)slot * d.Pp + p];
+                    if (h > 0) gv[h] = rg[(size_t)slot * d.Pp + p];
+                }
+            }
+        }
+        const float ag = ratio_nn(g, gp);                         // utils_env.py:156-157
+        float *srow = stage + 4 + lane * OD;
+        if (ok) {
+            rg[(size_t)head * d.Pp + p] = ag;
+            s_absadjg += fabsf(ag);
+            s_gdiff += fabsf(g - gp);
+        }
+        if (HT > 0) {
+            gv[0] = ag;
+#pragma unroll
+            for (int h = 0; h < HB; ++h) {
+                if (ok) s_state += fabsf(wv[h]) + fabsf(gv[h]);
+                srow[h] = clip_only_m1(wv[h]);
+                srow[HB + h] = obsL[h];
+                srow[2 * HB + h] = clip_only_m1(gv[h]);
+            }
+        } else {
+            for (int h = 0; h < H; ++h) {
+                float w1 = 0.f, g1 = 0.f;
+                if (h < nvalid) {
+                    int slot = head - h;
+                    slot += slot < 0 ? H : 0;
+                    w1 = rw[(size_t)slot * d.Pp + p];
+                    g1 = h > 0 ? rg[(size_t)slot * d.Pp + p] : ag;
+                }
+                if (ok) s_state += fabsf(w1) + fabsf(g1);
+                srow[h] = clip_only_m1(w1);
+                srow[H + h] = obsL[h];
+                srow[2 * H + h] = clip_only_m1(g1);
+            }
+        }
+        __syncwarp();
+        // contiguous write of this warp's rows: [g_lo, g_hi) words of the obs tensor
+        const int nrows = min(32, d.P - rbase);
+        const size_t g_lo = ((size_t)e * d.P + rbase) * OD, g_hi = g_lo + (size_t)nrows * OD;
+        const int sh = (int)(g_lo & 3);                           // smem index = x - g_lo + 4
+        // stage + 4 holds word g_lo; 16-byte phase of smem (stage is 16B aligned, +4 words) is 0,
+        // of global it is sh: copy head words scalar, then aligned float4 with an smem shift
+        size_t b_lo = (g_lo + 3) & ~(size_t)3, b_hi = g_hi & ~(size_t)3;
+        if (b_lo >= b_hi) { b_lo = g_hi; b_hi = g_hi; }
+        const float *src = stage + 4;
+        for (size_t x = g_lo + lane; x < b_lo; x += 32) a.obs[x] = src[x - g_lo];
+        if (sh == 0) {
+            for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128)
+                *reinterpret_cast<float4 *>(a.obs + x) = *reinterpret_cast<const float4 *>(src + (x - g_lo));
+        } else {
+            for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128) {
+                const float *q = src + (x - g_lo);
+                *reinterpret_cast<float4 *>(a.obs + x) = make_float4(q[0], q[1], q[2], q[3]);
+            }
+        }
+        for (size_t x = b_hi + lane; x < g_hi; x += 32) a.obs[x] = src[x - g_lo];
+        __syncwarp();
+    }
     // per-segment partials (deterministic: fixed order inside the CTA, summed per env later)
-    __shared__ double red[2 * 4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double v0 = warp_sum((double)st.f[ST_ABSADJG]), v1 = warp_sum((double)st.f[ST_GDIFF]);
-    const double v2 = warp_sum((double)st.f[ST_STATE]);
+    __shared__ double red[OBS_WARPS * 4];
+    const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+    const double v2 = warp_sum((double)s_state);
     if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double *out = d.part + ((size_t)e * d.nseg + seg) * 4;
-        const int nw = blockDim.x >> 5;
         for (int i = 0; i < 3; ++i) {
             double v = 0.0;
-            for (int w = 0; w < nw; ++w) v += red[w * 4 + i];
+            for (int w = 0; w < OBS_WARPS; ++w) v += red[w * 4 + i];
             out[i] = v;
         }
     }
@@ -1278,11 +1353,10 @@ struct b2e_env {
     int nthreads, grid, num_sms;
     size_t smem_bytes;
     float *X, *targets_f;
-    int *labels, *ord, *perm, *row_of_param;
+    int *labels, *ord, *perm, *row_of_param, *param_of_row;
     float *w, *gprev, *gnext, *ringw, *ringg;
     double *part;
     EnvScalars *sc;
-    Dev d_obs;                       // Dev with the observation kernel's shared-memory layout
     size_t smem_obs;
     int chunk_envs;
     cudaStream_t side;               // the observation kernel runs here, next to the compute kernel
@@ -1401,7 +1475,7 @@ int configure(b2e_handle h) {
     d.off_red = off; off += round_up(fred > red_floats ? fred : red_floats, 4);
     // large problems: compute kernel + streaming observation kernel
     d.split = (d.P >= 4096 && c.env_kind == B2E_ENV_MULTIOPTLRS) ? 1 : 0;
-    d.nseg = (d.P + SEG_CHUNKS * 128 - 1) / (SEG_CHUNKS * 128);
+    d.nseg = (d.P + SEG_ROWS - 1) / SEG_ROWS;
     d.stage_stride = round_up(SPAN_CAP * d.OD + 8, 4);
     d.off_stage = off; off += d.split ? 0 : nw * d.stage_stride;
     d.off_rows = off; off += d.split ? 0 : nw * (128 + SPAN_CAP);
@@ -1410,14 +1484,7 @@ int configure(b2e_handle h) {
     d.off_lb = off; off += round_up(d.B, 4);
     d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
     h->smem_bytes = (size_t)off * sizeof(float);
-    // observation kernel: 2 warps, each with its own staging
-    h->d_obs = d;
-    Dev &o = h->d_obs;
-    const int nw2 = 2;
-    o.off_stage = 0;
-    o.off_rows = nw2 * o.stage_stride;
-    o.off_misc = o.off_rows + nw2 * (128 + SPAN_CAP);
-    h->smem_obs = (size_t)(o.off_misc + B2E_MAX_HISTORY) * sizeof(float);
+    h->smem_obs = (size_t)(B2E_MAX_HISTORY + OBS_WARPS * (32 * d.OD + 8)) * sizeof(float);
     return 0;
 }
 
@@ -1475,7 +1542,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->cfg = *cfg;
     h->launches = 0;
     h->dataset_bound = h->stream_bound = false;
-    h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = nullptr;
+    h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr;
     h->side = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
@@ -1547,19 +1614,23 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         const std::string err = lex_rows(d.P, rows);
         bool ok = err.empty() && dmalloc((void **)&h->row_of_param, (size_t)d.Pp * 4) &&
                   cudaMemcpy(h->row_of_param, rows, (size_t)d.Pp * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        int *params = ok ? new (std::nothrow) int[d.Pp] : nullptr;
+        if (params) {
+            for (int i = 0; i < d.Pp; ++i) params[i] = 0;
+            for (int i = 0; i < d.P; ++i) params[rows[i]] = i;
+            ok = dmalloc((void **)&h->param_of_row, (size_t)d.Pp * 4) &&
+                 cudaMemcpy(h->param_of_row, params, (size_t)d.Pp * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+            delete[] params;
+        } else {
+            ok = false;
+        }
         delete[] rows;
         if (!ok) return bail("b2e_create: row table: " + err);
     }
     d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
     d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part;
     d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
-    d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param;
-    {
-        Dev &o = h->d_obs;
-        o.X = d.X; o.labels = d.labels; o.targets = d.targets; o.w = d.w; o.gprev = d.gprev;
-        o.gnext = d.gnext; o.part = d.part; o.ringw = d.ringw; o.ringg = d.ringg; o.sc = d.sc;
-        o.ord = d.ord; o.perm = d.perm; o.perm_stride = d.perm_stride; o.row_of_param = d.row_of_param;
-    }
+    d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param; d.param_of_row = h->param_of_row;
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
@@ -1569,7 +1640,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
 void b2e_destroy(b2e_handle h) {
     if (!h) return;
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
-    cudaFree(h->row_of_param); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
+    cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
     cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1664,10 +1735,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         cudaEvent_t ev = h->ev_chunk[chunk & 63];
         CUDA_TRY(h, cudaEventRecord(ev, main_s));
         CUDA_TRY(h, cudaStreamWaitEvent(h->side, ev, 0));
-        h->d_obs.gprev = d.gprev; h->d_obs.gnext = d.gnext; h->d_obs.perm_stride = d.perm_stride;
         const dim3 grid(d.nseg, ec);
-        if (d.H == 5) obs_kernel<5><<<grid, 64, h->smem_obs, h->side>>>(h->d_obs, ac);
-        else obs_kernel<0><<<grid, 64, h->smem_obs, h->side>>>(h->d_obs, ac);
+        if (d.H == 5) obs_kernel<5><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
+        else obs_kernel<0><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
     }

@@ -38,7 +38,8 @@ def main():
     rep, so_path = sys.argv[1], sys.argv[2]
     kernel = sys.argv[3] if len(sys.argv) > 3 else 'optenv_kernel'
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], check=True,
+    out = subprocess.run(['ncu', '-i', rep, '--kernel-name', 'regex:' + kernel.split('I')[0].split('(')[0],
+                          '--page', 'source', '--csv'], check=True,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
