@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -65,10 +66,12 @@ struct Dev {
     long long perm_stride;
     const int *row_of_param;
     const int *param_of_row;
-    int off_T, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
+    int off_red2;
+    int off_T, off_T2, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
         off_y, off_lb, off_misc;
     int stage_stride, xslack;
     int split, nseg;
+    int fast, cg;                    // register-tiled GEMM path (N1 % 8 == 0, B <= 32, 256 threads)
 };
 
 struct StepArgs {
@@ -344,6 +347,167 @@ __device__ void g_compute(const Dev &d, const float *sm, float *T, int k0, int c
                 if (k0 + kl + j < d.D) T[(kl + j) * d.N1p + c] = acc[j];
         }
     }
+}
+
+// ------------------------------------------------ register-tiled variants (fast path)
+// Used when N1 is a multiple of 8 that divides the CTA into column groups (e.g. 64):
+// forward : thread = 4 samples x 8 columns, K split over the 4 quarters of the CTA;
+// backward: thread = 4 rows x 8 columns of the tile, all samples.
+// A thread's 8 columns are two runs of 4, N1/2 apart, so that a warp's float4 accesses
+// cover whole 128-byte lines.
+__device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *Xs, const float *T,
+                                                  int k0, int krows4, float (&acc)[4][8]) {
+    const int t = threadIdx.x;
+    const int per_slice = 8 * d.cg;                       // threads per K slice
+    const int q = t / per_slice, u = t - q * per_slice;
+    const int sg = u / d.cg, cgi = u - sg * d.cg;
+    const int nslices = blockDim.x / per_slice;
+    const int rows_per = ((krows4 / 4 + nslices - 1) / nslices) * 4;
+    const int kb = q * rows_per;
+    int ke = kb + rows_per;
+    ke = ke < krows4 ? ke : krows4;
+    const int half = d.N1 >> 1;
+    const float *xr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int s = sg + 8 * i;
+        s = s < d.B ? s : d.B - 1;
+        xr[i] = Xs + s * d.Ds + k0;
+    }
+    const float *tc = T + 4 * cgi;
+    for (int k = kb; k < ke; k += 4) {
+        float xv[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 x = *reinterpret_cast<const float4 *>(xr[i] + k);
+            xv[i][0] = x.x; xv[i][1] = x.y; xv[i][2] = x.z; xv[i][3] = x.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float *tr = tc + (k + kk) * d.N1p;
+            const float4 t0 = *reinterpret_cast<const float4 *>(tr);
+            const float4 t1 = *reinterpret_cast<const float4 *>(tr + half);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = xv[i][kk];
+                acc[i][0] = fmaf(x, t0.x, acc[i][0]);
+                acc[i][1] = fmaf(x, t0.y, acc[i][1]);
+                acc[i][2] = fmaf(x, t0.z, acc[i][2]);
+                acc[i][3] = fmaf(x, t0.w, acc[i][3]);
+                acc[i][4] = fmaf(x, t1.x, acc[i][4]);
+                acc[i][5] = fmaf(x, t1.y, acc[i][5]);
+                acc[i][6] = fmaf(x, t1.z, acc[i][6]);
+                acc[i][7] = fmaf(x, t1.w, acc[i][7]);
+            }
+        }
+    }
+}
+
+__device__ void f_store_fast(const Dev &d, float *sm, float (&acc)[4][8]) {
+    const int t = threadIdx.x;
+    const int per_slice = 8 * d.cg;
+    const int q = t / per_slice, u = t - q * per_slice;
+    const int sg = u / d.cg, cgi = u - sg * d.cg;
+    const int nslices = blockDim.x / per_slice;
+    const int half = d.N1 >> 1;
+    float *Hb = sm + d.off_H;
+    float *red = sm + d.off_red;
+    const int n = d.B * d.N1p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int s = sg + 8 * i;
+        if (s < d.B) {
+            float *dst = red + (size_t)q * n + s * d.N1p + 4 * cgi;
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            *reinterpret_cast<float4 *>(dst + half) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {
+        float v = 0.f;
+        for (int qq = 0; qq < nslices; ++qq) v += red[(size_t)qq * n + i];
+        Hb[i] = v;
+    }
+    __syncthreads();
+}
+
+__device__ void g_compute_fast(const Dev &d, const float *sm, float *T, int k0, int cnt) {
+    const int t = threadIdx.x;
+    const int rgi = t / d.cg, cgi = t - rgi * d.cg;
+    const int kl = rgi * 4;
+    if (kl >= d.KT || k0 + kl >= d.D) return;
+    const int half = d.N1 >> 1;
+    const float *xr = sm + k0 + kl;
+    const float *dp = sm + d.off_dP + 4 * cgi;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+    for (int s = 0; s < cnt; ++s) {
+        const float4 x = *reinterpret_cast<const float4 *>(xr + s * d.Ds);
+        const float4 d0 = *reinterpret_cast<const float4 *>(dp + s * d.N1p);
+        const float4 d1 = *reinterpret_cast<const float4 *>(dp + s * d.N1p + half);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j][0] = fmaf(xv[j], d0.x, acc[j][0]);
+            acc[j][1] = fmaf(xv[j], d0.y, acc[j][1]);
+            acc[j][2] = fmaf(xv[j], d0.z, acc[j][2]);
+            acc[j][3] = fmaf(xv[j], d0.w, acc[j][3]);
+            acc[j][4] = fmaf(xv[j], d1.x, acc[j][4]);
+            acc[j][5] = fmaf(xv[j], d1.y, acc[j][5]);
+            acc[j][6] = fmaf(xv[j], d1.z, acc[j][6]);
+            acc[j][7] = fmaf(xv[j], d1.w, acc[j][7]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (k0 + kl + j < d.D) {
+            float *dst = T + (kl + j) * d.N1p + 4 * cgi;
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            *reinterpret_cast<float4 *>(dst + half) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Hpre = X . W1, W1 streamed from HBM through two tile buffers with cp.async
+__device__ void forward_from_global_fast(const Dev &d, float *sm, const float *wE) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+    float *const T0 = sm + d.off_T, *const T1 = sm + d.off_T2;
+    auto issue = [&](int t) {
+        const int k0 = t * d.KT;
+        const int krows = min(d.KT, d.D - k0);
+        const int nq = (krows * d.N1) >> 2;
+        const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * d.N1);
+        float4 *dst = reinterpret_cast<float4 *>((t & 1) ? T1 : T0);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue(0);
+    for (int t = 0; t < d.ntiles; ++t) {
+        const int k0 = t * d.KT;
+        const int krows = min(d.KT, d.D - k0), krows4 = (krows + 3) & ~3;
+        if (t + 1 < d.ntiles) { issue(t + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        float *T = (t & 1) ? T1 : T0;
+        for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
+        __syncthreads();
+        f_accumulate_fast(d, sm, T, k0, krows4, acc);
+        __syncthreads();
+    }
+    f_store_fast(d, sm, acc);
 }
 
 // ---------------------------------------------------------------------- the tail
@@ -787,17 +951,17 @@ __device__ void load_tail(const Dev &d, float *sm, const float *wE) {
 }
 
 // gradient of all parameters at the parameters currently in HBM / tw; PASS_R or PASS_E
-template <int PASS>
+template <int PASS, bool BIG>
 __device__ float eval_current(const Dev &d, const StepArgs &a, float *sm, const EpiCtx &cx,
                               int cnt, Stats &st) {
     load_tail(d, sm, cx.wE);
-    if (d.ntiles) forward_from_global(d, sm, cx.wE);
+    if (d.ntiles) { if (BIG && d.fast) forward_from_global_fast(d, sm, cx.wE); else forward_from_global(d, sm, cx.wE); }
     const float loss = tail_eval(d, sm, cnt);
     float *T = sm + d.off_T;
     epilogue<PASS, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
     for (int t = 0; t < d.ntiles; ++t) {
         const int k0 = t * d.KT;
-        g_compute(d, sm, T, k0, cnt);
+        if (BIG && d.fast) g_compute_fast(d, sm, T, k0, cnt); else g_compute(d, sm, T, k0, cnt);
         __syncthreads();
         epilogue<PASS, 0>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
         __syncthreads();
@@ -818,6 +982,7 @@ __device__ void make_ctx(const Dev &d, int e, EpiCtx &cx) {
 }
 
 // base_reset (multioptlrs.py:66-78) of one env
+template <bool BIG>
 __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     EnvScalars *sc = d.sc + e;
     EpiCtx cx;
@@ -845,9 +1010,9 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     __syncthreads();
     Stats st;
     zero_stats(st);
-    const float loss = eval_current<PASS_R>(d, a, sm, cx, cnt, st);
+    const float loss = eval_current<PASS_R, BIG>(d, a, sm, cx, cnt, st);
     Totals tot;
-    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red));
+    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
         for (int i = 0; i < B2E_MAX_HISTORY; ++i) sc->adj_loss[i] = 0.f;
@@ -868,7 +1033,7 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     __syncthreads();
 }
 
-template <int HT>
+template <int HT, bool BIG>
 __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     EnvScalars *sc = d.sc + e;
     EpiCtx cx;
@@ -888,7 +1053,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
 
     // ---- gradient at w_{t-1}, update, forward at w_t (fused per tile)
     load_tail(d, sm, cx.wE);
-    if (d.ntiles) forward_from_global(d, sm, cx.wE);
+    if (d.ntiles) { if (BIG && d.fast) forward_from_global_fast(d, sm, cx.wE); else forward_from_global(d, sm, cx.wE); }
     tail_eval(d, sm, cnt);
     epilogue<PASS_U, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
     __syncthreads();
@@ -901,7 +1066,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     for (int t = 0; t < d.ntiles; ++t) {
         const int k0 = t * d.KT;
         const int krows = min(d.KT, d.D - k0), krows4 = (krows + 3) & ~3;
-        g_compute(d, sm, T, k0, cnt);
+        if (BIG && d.fast) g_compute_fast(d, sm, T, k0, cnt); else g_compute(d, sm, T, k0, cnt);
         __syncthreads();
         epilogue<PASS_U, 0>(d, a, sm, cx, k0 * d.N1, (k0 + krows) * d.N1, T, true, k0, st);
         for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
@@ -911,10 +1076,10 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
                 T[k * d.N1p + c] = 0.f;
             }
         __syncthreads();
-        f_accumulate(d, sm, T, k0, krows4, acc);
+        if (BIG && d.fast) f_accumulate_fast(d, sm, T, k0, krows4, acc); else f_accumulate(d, sm, T, k0, krows4, acc);
         __syncthreads();
     }
-    if (d.ntiles) f_store(d, sm, acc);
+    if (d.ntiles) { if (BIG && d.fast) f_store_fast(d, sm, acc); else f_store(d, sm, acc); }
     __syncthreads();
 
     // ---- gradient and loss at w_t
@@ -940,7 +1105,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         epilogue<PASS_S, 0>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
         for (int t = 0; t < d.ntiles; ++t) {
             const int k0 = t * d.KT;
-            g_compute(d, sm, T, k0, cnt);
+            if (BIG && d.fast) g_compute_fast(d, sm, T, k0, cnt); else g_compute(d, sm, T, k0, cnt);
             __syncthreads();
             epilogue<PASS_S, 0>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
             __syncthreads();
@@ -949,14 +1114,14 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
         epilogue<PASS_G, HT>(d, a, sm, cx, d.P1, d.P, sm + d.off_tg, false, 0, st);
         for (int t = 0; t < d.ntiles; ++t) {
             const int k0 = t * d.KT;
-            g_compute(d, sm, T, k0, cnt);
+            if (BIG && d.fast) g_compute_fast(d, sm, T, k0, cnt); else g_compute(d, sm, T, k0, cnt);
             __syncthreads();
             epilogue<PASS_G, HT>(d, a, sm, cx, k0 * d.N1, min(d.D, k0 + d.KT) * d.N1, T, true, k0, st);
             __syncthreads();
         }
     }
     Totals tot;
-    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red));
+    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
 
     // ---- scalars: reward, done, info, history bookkeeping (thread 0)
     bool done = false;
@@ -1030,9 +1195,10 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     done = misc[1] != 0.f;
     __syncthreads();
     if (wrap) shuffle_order(d, e, sc);
-    if (done && d.auto_reset && !d.split) reset_env(d, a, sm, e);
+    if (done && d.auto_reset && !d.split) reset_env<BIG>(d, a, sm, e);
 }
 
+template <bool BIG>
 __device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     EnvScalars *sc = d.sc + e;
     EpiCtx cx;
@@ -1042,23 +1208,23 @@ __device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
     Stats st;
     zero_stats(st);
-    const float loss = eval_current<PASS_E>(d, a, sm, cx, cnt, st);
+    const float loss = eval_current<PASS_E, BIG>(d, a, sm, cx, cnt, st);
     if (threadIdx.x == 0) a.loss_out[e] = loss;
     __syncthreads();
 }
 
-template <int HT>
-__global__ void __launch_bounds__(512) optenv_kernel(const __grid_constant__ Dev d,
+template <int HT, bool BIG>
+__global__ void __launch_bounds__(256, BIG ? 1 : 2) optenv_kernel(const __grid_constant__ Dev d,
                                                      const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int e_end = a.e_begin + a.e_count;
     for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
         if (a.mode == MODE_STEP) {
-            step_env<HT>(d, a, sm, e);
+            step_env<HT, BIG>(d, a, sm, e);
         } else if (a.mode == MODE_RESET) {
-            if (a.mask == nullptr || a.mask[e]) reset_env(d, a, sm, e);
+            if (a.mask == nullptr || a.mask[e]) reset_env<BIG>(d, a, sm, e);
         } else {
-            eval_env(d, a, sm, e);
+            eval_env<BIG>(d, a, sm, e);
         }
         __syncthreads();
     }
@@ -1078,14 +1244,19 @@ template <int HT>
 __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_constant__ Dev d,
                                                              const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int e = a.e_begin + blockIdx.y;
-    const int seg = blockIdx.x;
+    __shared__ double red[OBS_WARPS * 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const EnvScalars *sc = d.sc + e;
     const int H = HT > 0 ? HT : d.H, OD = d.OD;
     float *obsL = sm;                                         // [B2E_MAX_HISTORY]
     float *stage = sm + B2E_MAX_HISTORY + warp * (32 * OD + 8);
+    // persistent CTAs: a fixed number per SM so that the compute kernel always finds room
+    const int nitems = a.e_count * d.nseg;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int e = a.e_begin + item / d.nseg;
+    const int seg = item - (item / d.nseg) * d.nseg;
+    const EnvScalars *sc = d.sc + e;
     const int head = sc->head, nvalid = sc->nvalid;          // already advanced by the compute kernel
+    __syncthreads();
     if (threadIdx.x < H) {
         const int h = threadIdx.x;
         float v = 0.f;
@@ -1178,7 +1349,6 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_consta
         __syncwarp();
     }
     // per-segment partials (deterministic: fixed order inside the CTA, summed per env later)
-    __shared__ double red[OBS_WARPS * 4];
     const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
     const double v2 = warp_sum((double)s_state);
     if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
@@ -1191,6 +1361,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_consta
             out[i] = v;
         }
     }
+    }   // item loop
 }
 
 // info entries that need the observation kernel's partial sums (states_*, adjusted_grad, grad_diff)
@@ -1358,8 +1529,9 @@ struct b2e_env {
     double *part;
     EnvScalars *sc;
     size_t smem_obs;
-    int chunk_envs;
-    cudaStream_t side;               // the observation kernel runs here, next to the compute kernel
+    int chunk_envs, obs_grid;
+    cudaStream_t side;               // the observation kernel runs here (lowest priority) ...
+    cudaStream_t hi;                 // ... next to the compute kernel (highest priority)
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_chunk[64];
     bool dataset_bound, stream_bound;
@@ -1447,6 +1619,15 @@ int configure(b2e_handle h) {
     d.gcc = d.N1 > 32 ? (d.N1 + 31) / 32 : 1;
     d.KT = d.KR > 64 ? d.KR : 64;
     d.ntiles = d.D > 0 ? (d.D + d.KT - 1) / d.KT : 0;
+    // register-tiled path: N1/8 column groups must tile the 256-thread CTA
+    d.cg = d.N1 / 8;
+    d.fast = (d.kind != B2E_PROBLEM_FUNC && d.N1 % 8 == 0 && d.cg >= 4 && d.cg <= 32 &&
+              256 % d.cg == 0 && d.B <= 32 && (long long)d.P >= 4096) ? 1 : 0;
+    if (d.fast) {
+        const int rows_max = 4 * (256 / d.cg);                 // tile rows one backward pass covers
+        d.ntiles = (d.D + rows_max - 1) / rows_max;
+        d.KT = round_up((d.D + d.ntiles - 1) / d.ntiles, 4);   // e.g. D = 784 -> 7 tiles of 112 rows
+    }
     // threads: small problems use small CTAs so that several fit one SM
     const long long work = (long long)d.P;
     h->nthreads = work >= 4096 ? 256 : (work >= 512 ? 128 : 64);
@@ -1454,17 +1635,19 @@ int configure(b2e_handle h) {
     // forward decomposition
     d.nsc = (d.B + 31) / 32;
     d.ncc = d.N1p / 8;
-    while (d.nsc * d.ncc > nw * MAXI && h->nthreads < 512) { h->nthreads *= 2; nw *= 2; }
+    while (d.nsc * d.ncc > nw * MAXI && h->nthreads < 256) { h->nthreads *= 2; nw *= 2; }
     if (d.nsc * d.ncc > nw * MAXI)
         return fail(h, "batch_size x layer width too large for the fused kernel "
-                       "(need ceil(B/32) * ceil(N1/8) <= 64)");
+                       "(need ceil(B/32) * ceil(N1/8) <= 32)");
     d.nks = 1;
-    while (d.nsc * d.ncc * d.nks * 2 <= nw && d.KT / (d.nks * 2) >= 4) d.nks *= 2;
+    while (d.nsc * d.ncc * d.nks * 2 <= nw && d.KT / (d.nks * 2) >= 4 && !d.fast) d.nks *= 2;
     d.fitems = d.nsc * d.ncc * d.nks;
+    if (d.fast) d.nks = 256 / (8 * d.cg);                      // K slices of the fast forward
     // shared memory carve-up (float offsets, all multiples of 4)
     d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
     int off = d.B * d.Ds + d.xslack;
-    d.off_T = off; off += d.KT * d.N1p;
+    d.off_T = off; off += round_up(d.KT, 4) * d.N1p;
+    d.off_T2 = off; off += d.fast ? round_up(d.KT, 4) * d.N1p : 0;
     d.off_H = off; off += round_up(d.B * d.N1p, 4);
     d.off_dP = off; off += round_up(d.B * d.N1p, 4);
     d.off_tw = off; off += round_up(d.tailP, 4);
@@ -1472,7 +1655,13 @@ int configure(b2e_handle h) {
     d.off_Z = off; off += d.hidden ? round_up(d.B * d.Cp, 4) : 0;
     const int red_floats = 2 * NSTAT * 16;
     const int fred = d.nks > 1 ? d.nks * d.B * d.N1p : 0;
-    d.off_red = off; off += round_up(fred > red_floats ? fred : red_floats, 4);
+    if (d.fast && fred <= 2 * round_up(d.KT, 4) * d.N1p) {
+        d.off_red = d.off_T;            // tiles are idle when the forward partials are reduced ...
+        d.off_red2 = off; off += red_floats;                       // ... the statistics scratch is not
+    } else {
+        d.off_red = off; off += round_up(fred > red_floats ? fred : red_floats, 4);
+        d.off_red2 = d.off_red;
+    }
     // large problems: compute kernel + streaming observation kernel
     d.split = (d.P >= 4096 && c.env_kind == B2E_ENV_MULTIOPTLRS) ? 1 : 0;
     d.nseg = (d.P + SEG_ROWS - 1) / SEG_ROWS;
@@ -1490,10 +1679,14 @@ int configure(b2e_handle h) {
 
 int launch(b2e_handle h, StepArgs args, void *stream) {
     if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
-    if (h->d.H == 5)
-        optenv_kernel<5><<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
-    else
-        optenv_kernel<0><<<h->grid, h->nthreads, h->smem_bytes, (cudaStream_t)stream>>>(h->d, args);
+    const cudaStream_t cs = (cudaStream_t)stream;
+    if (h->d.fast) {
+        if (h->d.H == 5) optenv_kernel<5, true><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
+        else optenv_kernel<0, true><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
+    } else {
+        if (h->d.H == 5) optenv_kernel<5, false><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
+        else optenv_kernel<0, false><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
+    }
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -1544,7 +1737,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->dataset_bound = h->stream_bound = false;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr;
-    h->side = nullptr; h->ev_fork = h->ev_join = nullptr;
+    h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
     if (cudaSetDevice(cfg->device) != cudaSuccess) return bail("b2e_create: cudaSetDevice failed");
@@ -1555,15 +1748,15 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return bail("b2e_create: problem does not fit the fused kernel's shared memory (" +
                     std::to_string(h->smem_bytes) + " bytes needed)");
-    if (cudaFuncSetAttribute(optenv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)h->smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(optenv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const void *kernel_fn = h->d.fast
+        ? (cfg->max_history == 5 ? (const void *)optenv_kernel<5, true> : (const void *)optenv_kernel<0, true>)
+        : (cfg->max_history == 5 ? (const void *)optenv_kernel<5, false> : (const void *)optenv_kernel<0, false>);
+    if (cudaFuncSetAttribute(kernel_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)h->smem_bytes) != cudaSuccess)
         return bail("b2e_create: cudaFuncSetAttribute(smem) failed");
     int occ = 0;
-    cudaError_t occ_err = cfg->max_history == 5
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel<5>, h->nthreads, h->smem_bytes)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, optenv_kernel<0>, h->nthreads, h->smem_bytes);
+    cudaError_t occ_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_fn, h->nthreads,
+                                                                        h->smem_bytes);
     if (occ_err != cudaSuccess || occ < 1)
         return bail("b2e_create: kernel does not fit an SM");
     const long long resident = (long long)occ * h->num_sms;
@@ -1580,7 +1773,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             !dmalloc((void **)&h->part, (size_t)d.E * d.nseg * 4 * sizeof(double)))
             return bail("b2e_create: cudaMalloc of the split-path buffers failed");
         cudaMemset(h->gnext, 0, EP * 4);
-        if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
             return bail("b2e_create: stream/event creation failed");
@@ -1592,7 +1788,12 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_obs) != cudaSuccess)
             return bail("b2e_create: observation kernel does not fit (max_history too large)");
+        // kernels that share an SM must agree on its L1/shared-memory split
+        cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(kernel_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         h->chunk_envs = 4 * h->num_sms;
+        h->obs_grid = 2 * h->num_sms;
     }
     cudaMemset(h->w, 0, EP * 4); cudaMemset(h->gprev, 0, EP * 4);
     cudaMemset(h->ringw, 0, EP * d.H * 4); cudaMemset(h->ringg, 0, EP * d.H * 4);
@@ -1643,6 +1844,7 @@ void b2e_destroy(b2e_handle h) {
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
     cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->hi) cudaStreamDestroy(h->hi);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
@@ -1726,20 +1928,39 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     Dev &d = h->d;
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_s));
     CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
     int chunk = 0;
+    static const bool trace = getenv("B2E_TRACE") != nullptr;      // debug: per-kernel timeline
+    cudaEvent_t tr[4][16];
+    if (trace) for (auto &row : tr) for (auto &ev : row) cudaEventCreate(&ev);
+    if (trace) cudaEventRecord(tr[0][15], h->hi);
     for (int e0 = 0; e0 < d.E; e0 += h->chunk_envs, ++chunk) {
         const int ec = d.E - e0 < h->chunk_envs ? d.E - e0 : h->chunk_envs;
         StepArgs ac = a;
         ac.e_begin = e0; ac.e_count = ec;
-        if (launch(h, ac, main_s)) return 1;
+        if (trace && chunk < 15) cudaEventRecord(tr[0][chunk], h->hi);
+        if (launch(h, ac, h->hi)) return 1;
+        if (trace && chunk < 15) cudaEventRecord(tr[1][chunk], h->hi);
         cudaEvent_t ev = h->ev_chunk[chunk & 63];
-        CUDA_TRY(h, cudaEventRecord(ev, main_s));
+        CUDA_TRY(h, cudaEventRecord(ev, h->hi));
         CUDA_TRY(h, cudaStreamWaitEvent(h->side, ev, 0));
-        const dim3 grid(d.nseg, ec);
+        const int items = d.nseg * ec;
+        const int grid = items < h->obs_grid ? items : h->obs_grid;
+        if (trace && chunk < 15) cudaEventRecord(tr[2][chunk], h->side);
         if (d.H == 5) obs_kernel<5><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
         else obs_kernel<0><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
+        if (trace && chunk < 15) cudaEventRecord(tr[3][chunk], h->side);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
+    }
+    if (trace) {
+        cudaDeviceSynchronize();
+        for (int c = 0; c < chunk && c < 15; ++c) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0][15], tr[k][c]);
+            fprintf(stderr, "chunk %d: compute %.3f..%.3f ms   observe %.3f..%.3f ms\n", c, t[0], t[1], t[2], t[3]);
+        }
+        for (auto &row : tr) for (auto &ev : row) cudaEventDestroy(ev);
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
     CUDA_TRY(h, cudaStreamWaitEvent(main_s, h->ev_join, 0));
