@@ -72,6 +72,9 @@ struct Dev {
     int stage_stride, xslack;
     int split, nseg;
     int fast, cg;                    // register-tiled GEMM path (N1 % 8 == 0, B <= 32, 256 threads)
+    int ev_X0, ev_X1, ev_W0, ev_W1, ev_XS;   // eval kernel: streamed X / W tile buffers
+    int nsegU;
+    double *part_u;
 };
 
 struct StepArgs {
@@ -355,8 +358,8 @@ __device__ void g_compute(const Dev &d, const float *sm, float *T, int k0, int c
 // backward: thread = 4 rows x 8 columns of the tile, all samples.
 // A thread's 8 columns are two runs of 4, N1/2 apart, so that a warp's float4 accesses
 // cover whole 128-byte lines.
-__device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *Xs, const float *T,
-                                                  int k0, int krows4, float (&acc)[4][8]) {
+__device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xbase, int xstride,
+                                                  const float *T, int krows4, float (&acc)[4][8]) {
     const int t = threadIdx.x;
     const int per_slice = 8 * d.cg;                       // threads per K slice
     const int q = t / per_slice, u = t - q * per_slice;
@@ -372,7 +375,7 @@ __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *Xs,
     for (int i = 0; i < 4; ++i) {
         int s = sg + 8 * i;
         s = s < d.B ? s : d.B - 1;
-        xr[i] = Xs + s * d.Ds + k0;
+        xr[i] = xbase + s * xstride;
     }
     const float *tc = T + 4 * cgi;
     for (int k = kb; k < ke; k += 4) {
@@ -504,7 +507,7 @@ __device__ void forward_from_global_fast(const Dev &d, float *sm, const float *w
         float *T = (t & 1) ? T1 : T0;
         for (int i = krows * d.N1p + threadIdx.x; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
         __syncthreads();
-        f_accumulate_fast(d, sm, T, k0, krows4, acc);
+        f_accumulate_fast(d, sm + k0, d.Ds, T, krows4, acc);
         __syncthreads();
     }
     f_store_fast(d, sm, acc);
@@ -1076,7 +1079,7 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
                 T[k * d.N1p + c] = 0.f;
             }
         __syncthreads();
-        if (BIG && d.fast) f_accumulate_fast(d, sm, T, k0, krows4, acc); else f_accumulate(d, sm, T, k0, krows4, acc);
+        if (BIG && d.fast) f_accumulate_fast(d, sm + k0, d.Ds, T, krows4, acc); else f_accumulate(d, sm, T, k0, krows4, acc);
         __syncthreads();
     }
     if (d.ntiles) { if (BIG && d.fast) f_store_fast(d, sm, acc); else f_store(d, sm, acc); }
@@ -1364,7 +1367,279 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_consta
     }   // item loop
 }
 
-// info entries that need the observation kernel's partial sums (states_*, adjusted_grad, grad_diff)
+// =========================================================================================
+// Large problems: the step is a pipeline of four kernels on the caller's stream
+//   eval_kernel<false> : g0 = grad(batch, w_{t-1})                      (2 CTAs/SM, FFMA bound)
+//   update_kernel      : w_t = w_{t-1} - g0*lr(a); adj_w ring; stats    (streaming, HBM bound)
+//   eval_kernel<true>  : g_t, L_t = grad/loss(batch, w_t); scalars      (2 CTAs/SM, FFMA bound)
+//   obs_kernel         : adj_g ring + observation rows + stats          (streaming, HBM bound)
+// The eval kernel streams BOTH operands through double-buffered shared-memory tiles
+// (cp.async), so it needs ~110 KB per CTA and is insensitive to HBM latency.
+// =========================================================================================
+template <bool SECOND>
+__global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ Dev d,
+                                                      const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    float *const X0 = sm + d.ev_X0, *const X1 = sm + d.ev_X1;
+    float *const W0 = sm + d.ev_W0, *const W1 = sm + d.ev_W1;
+    float *misc = sm + d.off_misc;
+    const int XS = d.ev_XS;
+    const int e_end = a.e_begin + a.e_count;
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        EnvScalars *sc = d.sc + e;
+        const float *wE = d.w + (size_t)e * d.Pp;
+        float *gout = d.gnext + (size_t)e * d.Pp;
+        const int *idx; int cnt;
+        current_batch(d, a, e, sc, idx, cnt);
+        int *idx_s = reinterpret_cast<int *>(sm + d.off_idx);
+        int *ys = reinterpret_cast<int *>(sm + d.off_y);
+        for (int r = tid; r < d.B; r += blockDim.x) {
+            const int row = (r < cnt) ? idx[r] : 0;
+            idx_s[r] = row;
+            if (d.kind == B2E_PROBLEM_SOFTMAX) ys[r] = (r < cnt) ? d.labels[row] : 0;
+        }
+        if (d.kind == B2E_PROBLEM_LINREG) {
+            float *yt = sm + d.off_y;
+            for (int i = tid; i < d.B * d.C; i += blockDim.x) {
+                const int r = i / d.C, c = i - r * d.C;
+                yt[i] = (r < cnt) ? d.targets[(size_t)idx[r] * d.C + c] : 0.f;
+            }
+        }
+        for (int i = tid; i < 2 * d.B * XS; i += blockDim.x) X0[i] = 0.f;    // X0, X1 contiguous
+        for (int i = tid; i < d.tailP; i += blockDim.x) sm[d.off_tw + i] = wE[d.P1 + i];
+        __syncthreads();
+
+        auto issue_x = [&](int t) {
+            const int k0 = t * d.KT;
+            const int kq = (min(d.KT, d.Dp - k0)) >> 2;          // 16-byte chunks per row
+            float *dst = (t & 1) ? X1 : X0;
+            for (int i = tid; i < cnt * kq; i += blockDim.x) {
+                const int r = i / kq, c = i - r * kq;
+                cp_async16(dst + r * XS + 4 * c, d.X + (size_t)idx_s[r] * d.Dp + k0 + 4 * c);
+            }
+        };
+        auto issue_w = [&](int t) {
+            const int k0 = t * d.KT;
+            const int nq = (min(d.KT, d.D - k0) * d.N1) >> 2;
+            const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * d.N1);
+            float4 *dst = reinterpret_cast<float4 *>((t & 1) ? W1 : W0);
+            for (int i = tid; i < nq; i += blockDim.x) cp_async16(dst + i, src + i);
+        };
+
+        // ---- forward: Hpre = X . W1
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+        issue_x(0); issue_w(0); cp_async_commit();
+        for (int t = 0; t < d.ntiles; ++t) {
+            const int krows = min(d.KT, d.D - t * d.KT), krows4 = (krows + 3) & ~3;
+            if (t + 1 < d.ntiles) { issue_x(t + 1); issue_w(t + 1); cp_async_commit(); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            float *T = (t & 1) ? W1 : W0;
+            for (int i = krows * d.N1p + tid; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
+            __syncthreads();
+            f_accumulate_fast(d, (t & 1) ? X1 : X0, XS, T, krows4, acc);
+            __syncthreads();
+        }
+        f_store_fast(d, sm, acc);                            // partials reduced through the W tiles
+        // the first X tile of the backward pass can already travel
+        issue_x(0); cp_async_commit();
+        const float loss = tail_eval(d, sm, cnt);
+
+        // ---- backward: tail gradient, then g = X^T . dPre tile by tile, straight to HBM
+        float gsum = 0.f;
+        for (int i = tid; i < d.tailP; i += blockDim.x) {
+            const float g = sm[d.off_tg + i];
+            gout[d.P1 + i] = g;
+            gsum += g;
+        }
+        const int rgi = tid / d.cg, cgi = tid - rgi * d.cg, kl = rgi * 4;
+        const int half = d.N1 >> 1;
+        const float *dp = sm + d.off_dP + 4 * cgi;
+        for (int t = 0; t < d.ntiles; ++t) {
+            const int k0 = t * d.KT;
+            if (t + 1 < d.ntiles) { issue_x(t + 1); cp_async_commit(); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+            if (kl < d.KT && k0 + kl < d.D) {
+                const float *xr = ((t & 1) ? X1 : X0) + kl;
+                float g[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) g[j][c] = 0.f;
+                for (int s = 0; s < cnt; ++s) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xr + s * XS);
+                    const float4 d0 = *reinterpret_cast<const float4 *>(dp + s * d.N1p);
+                    const float4 d1 = *reinterpret_cast<const float4 *>(dp + s * d.N1p + half);
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        g[j][0] = fmaf(xv[j], d0.x, g[j][0]);
+                        g[j][1] = fmaf(xv[j], d0.y, g[j][1]);
+                        g[j][2] = fmaf(xv[j], d0.z, g[j][2]);
+                        g[j][3] = fmaf(xv[j], d0.w, g[j][3]);
+                        g[j][4] = fmaf(xv[j], d1.x, g[j][4]);
+                        g[j][5] = fmaf(xv[j], d1.y, g[j][5]);
+                        g[j][6] = fmaf(xv[j], d1.z, g[j][6]);
+                        g[j][7] = fmaf(xv[j], d1.w, g[j][7]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k0 + kl + j < d.D) {
+                        float *dst = gout + (size_t)(k0 + kl + j) * d.N1 + 4 * cgi;
+                        *reinterpret_cast<float4 *>(dst) = make_float4(g[j][0], g[j][1], g[j][2], g[j][3]);
+                        *reinterpret_cast<float4 *>(dst + half) = make_float4(g[j][4], g[j][5], g[j][6], g[j][7]);
+                        gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (!SECOND) continue;
+
+        // ---- scalars of the step (thread 0): history bookkeeping, reward, done, info
+        Stats st;
+        zero_stats(st);
+        st.f[ST_G] = gsum;
+        Totals tot;
+        block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
+        if (tid == 0) {
+            const int head_new = (sc->head + 1) % d.H;
+            const int nvalid_new = min(sc->nvalid + 1, d.H);
+            const double adjl = nan_to_num_d((double)loss / fabs((double)sc->loss_prev));
+            double reward;
+            switch (d.rew_ver) {                                       // utils_env.py:71-99
+                case 0: reward = -adjl; break;
+                case 1: reward = (double)(1.0f / loss); break;
+                case 2: reward = -adjl * 100.0; break;
+                case 3: reward = (double)(1.0f / loss) * 100.0; break;
+                case 4: reward = (double)logf(1.0f / loss); break;
+                case 5: reward = -(adjl - 1.0) * (adjl - 1.0); break;
+                default: reward = -(adjl - 1.0); break;
+            }
+            reward = fmin(fmax(reward, -100.0), 100.0);                // multioptlrs.py:103
+            const int step = sc->step + 1;                             // baseenvironment.py:37
+            bool done = step >= d.max_batches;
+            if (!done && loss > 1e4f) {                                // multioptlrs.py:105-107
+                done = true;
+                reward -= (double)(d.max_batches - step);
+            }
+            const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
+            sc->raw_pos = rp;
+            sc->raw_loss[rp] = loss;
+            sc->raw_gsum[rp] = tot.v[ST_G];
+            sc->loss_prev = loss;
+            sc->adj_loss[head_new] = (float)adjl;
+            sc->head = head_new;
+            sc->nvalid = nvalid_new;
+            sc->step = step;
+            double gs = 0.0, ls = 0.0;
+            for (int i = 0; i < RAW_DEPTH; ++i) { gs += sc->raw_gsum[i]; ls += (double)sc->raw_loss[i]; }
+            double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
+            info[0] = done ? (double)loss : nan("");                   // multioptlrs.py:108-110
+            info[1] = (double)loss;
+            info[8] = gs / (RAW_DEPTH * (double)d.P);
+            info[9] = gs;
+            info[10] = ls / RAW_DEPTH;
+            info[11] = adjl;
+            info[14] = reward;                                         // baseenvironment.py:40
+            info[15] = (double)step;
+            a.reward[e] = (float)reward;
+            a.done[e] = done ? 1 : 0;
+            if (d.index_mode == B2E_INDEX_INTERNAL) {
+                const int cur = sc->cursor + 1;                        // optimize_nn.py:102-112
+                misc[4] = (cur * d.B >= d.N) ? 1.f : 0.f;
+                sc->cursor = (cur * d.B >= d.N) ? 0 : cur;
+            } else {
+                misc[4] = 0.f;
+            }
+        }
+        __syncthreads();
+        const bool wrap = misc[4] != 0.f;
+        __syncthreads();
+        if (wrap) shuffle_order(d, e, sc);
+    }
+}
+
+// w_t = w_{t-1} - g0 * lr(action)  (multioptlrs.py:86-87), adjusted-weight ring, statistics.
+constexpr int UPD_QUADS = 4;                      // float4 groups per thread
+constexpr int UPD_SEG = 256 * UPD_QUADS * 4;      // parameters per CTA
+
+__global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Dev d,
+                                                     const __grid_constant__ StepArgs a) {
+    const int e = a.e_begin + blockIdx.y;
+    const int seg = blockIdx.x;
+    const EnvScalars *sc = d.sc + e;
+    const int head_new = (sc->head + 1) % d.H;
+    float *wE = d.w + (size_t)e * d.Pp;
+    const float *gE = d.gnext + (size_t)e * d.Pp;             // g0, left there by the first eval
+    float *rw = d.ringw + ((size_t)e * d.H + head_new) * d.Pp;
+    const float *act = a.actions + (size_t)e * d.P;
+    float4 w4[UPD_QUADS], g4[UPD_QUADS];
+    int4 r4[UPD_QUADS];
+    int pq[UPD_QUADS];
+#pragma unroll
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        pq[i] = seg * UPD_SEG + (i * 256 + threadIdx.x) * 4;
+        if (pq[i] < d.P) {
+            w4[i] = *reinterpret_cast<const float4 *>(wE + pq[i]);
+            g4[i] = *reinterpret_cast<const float4 *>(gE + pq[i]);
+            r4[i] = d.row_lex ? *reinterpret_cast<const int4 *>(d.row_of_param + pq[i])
+                              : make_int4(pq[i], pq[i] + 1, pq[i] + 2, pq[i] + 3);
+        }
+    }
+    float av[UPD_QUADS][4];
+#pragma unroll
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        const int rows[4] = {r4[i].x, r4[i].y, r4[i].z, r4[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) av[i][j] = (pq[i] + j < d.P) ? act[rows[j]] : 0.f;
+    }
+    float s_absw = 0.f;
+    double s_lr = 0.0, s_lr2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        if (pq[i] >= d.P) continue;
+        const float wv[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w};
+        const float gv[4] = {g4[i].x, g4[i].y, g4[i].z, g4[i].w};
+        float wn[4], aw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lr = action_to_lr(av[i][j], d.act_ver);
+            wn[j] = fmaf(-gv[j], lr, wv[j]);
+            aw[j] = ratio_nn(wn[j], wv[j]);                      // utils_env.py:158-159
+            if (pq[i] + j < d.P) {
+                s_absw += fabsf(wn[j]);
+                s_lr += (double)lr;
+                s_lr2 += (double)lr * (double)lr;
+            } else {
+                wn[j] = 0.f; aw[j] = 0.f;
+            }
+        }
+        *reinterpret_cast<float4 *>(wE + pq[i]) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+        *reinterpret_cast<float4 *>(rw + pq[i]) = make_float4(aw[0], aw[1], aw[2], aw[3]);
+    }
+    __shared__ double red[8 * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double v0 = warp_sum((double)s_absw), v1 = warp_sum(s_lr), v2 = warp_sum(s_lr2);
+    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *out = d.part_u + ((size_t)e * d.nsegU + seg) * 4;
+        for (int i = 0; i < 3; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[w * 4 + i];
+            out[i] = v;
+        }
+    }
+}
+
+// info entries that need the streaming kernels' partial sums (states_*, adjusted_grad, grad_diff)
 __global__ void info_finalize_kernel(Dev d, StepArgs a) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= d.E) return;
@@ -1380,9 +1655,21 @@ __global__ void info_finalize_kernel(Dev d, StepArgs a) {
         slot += slot < 0 ? d.H : 0;
         labs += (double)fabsf(sc->adj_loss[slot]);
     }
+    double absw = 0.0, lr = 0.0, lr2 = 0.0;
+    for (int s = 0; s < d.nsegU; ++s) {
+        const double *in = d.part_u + ((size_t)e * d.nsegU + s) * 4;
+        absw += in[0]; lr += in[1]; lr2 += in[2];
+    }
     const double P = (double)d.P;
     const double ssum = state + P * labs;
     double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
+    const double lr_mean = lr / P;
+    double lr_var = lr2 / P - lr_mean * lr_mean;
+    lr_var = lr_var > 0.0 ? lr_var : 0.0;
+    info[2] = absw / P;
+    info[3] = absw;
+    info[4] = lr_mean;
+    info[5] = sqrt(lr_var);
     info[6] = ssum / (P * (double)d.OD);
     info[7] = ssum;
     info[12] = absadjg / P;
@@ -1530,6 +1817,10 @@ struct b2e_env {
     EnvScalars *sc;
     size_t smem_obs;
     int chunk_envs, obs_grid;
+    Dev d_eval;                      // Dev with the eval kernel's shared-memory layout
+    size_t smem_eval;
+    int eval_grid;
+    double *part_u;
     cudaStream_t side;               // the observation kernel runs here (lowest priority) ...
     cudaStream_t hi;                 // ... next to the compute kernel (highest priority)
     cudaEvent_t ev_fork, ev_join;
@@ -1643,6 +1934,9 @@ int configure(b2e_handle h) {
     while (d.nsc * d.ncc * d.nks * 2 <= nw && d.KT / (d.nks * 2) >= 4 && !d.fast) d.nks *= 2;
     d.fitems = d.nsc * d.ncc * d.nks;
     if (d.fast) d.nks = 256 / (8 * d.cg);                      // K slices of the fast forward
+    // large problems run as a pipeline of kernels (eval / update / eval / observations)
+    d.split = (d.fast && c.env_kind == B2E_ENV_MULTIOPTLRS &&
+               d.nks * d.B * d.N1p <= 2 * round_up(d.KT, 4) * d.N1p) ? 1 : 0;
     // shared memory carve-up (float offsets, all multiples of 4)
     d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
     int off = d.B * d.Ds + d.xslack;
@@ -1663,7 +1957,6 @@ int configure(b2e_handle h) {
         d.off_red2 = d.off_red;
     }
     // large problems: compute kernel + streaming observation kernel
-    d.split = (d.P >= 4096 && c.env_kind == B2E_ENV_MULTIOPTLRS) ? 1 : 0;
     d.nseg = (d.P + SEG_ROWS - 1) / SEG_ROWS;
     d.stage_stride = round_up(SPAN_CAP * d.OD + 8, 4);
     d.off_stage = off; off += d.split ? 0 : nw * d.stage_stride;
@@ -1674,6 +1967,32 @@ int configure(b2e_handle h) {
     d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
     h->smem_bytes = (size_t)off * sizeof(float);
     h->smem_obs = (size_t)(B2E_MAX_HISTORY + OBS_WARPS * (32 * d.OD + 8)) * sizeof(float);
+    d.nsegU = (d.Pp + UPD_SEG - 1) / UPD_SEG;
+    {   // eval kernel: X and W1 both streamed through double-buffered tiles
+        h->d_eval = d;
+        Dev &v = h->d_eval;
+        const int kt4 = round_up(d.KT, 4);
+        v.ev_XS = ((kt4 >> 2) & 1) ? kt4 : kt4 + 4;              // odd number of float4 per row
+        int o = 0;
+        v.ev_X0 = o; o += d.B * v.ev_XS;
+        v.ev_X1 = o; o += d.B * v.ev_XS;
+        v.ev_W0 = o; o += kt4 * d.N1p;
+        v.ev_W1 = o; o += kt4 * d.N1p;
+        v.off_T = v.ev_W0; v.off_T2 = v.ev_W1;
+        v.off_red = v.ev_W0;                                     // forward partials: W tiles are idle then
+        v.off_H = o; o += round_up(d.B * d.N1p, 4);
+        v.off_dP = o; o += round_up(d.B * d.N1p, 4);
+        v.off_tw = o; o += round_up(d.tailP, 4);
+        v.off_tg = o; o += round_up(d.tailP, 4);
+        v.off_Z = o; o += d.hidden ? round_up(d.B * d.Cp, 4) : 0;
+        v.off_red2 = o; o += 2 * NSTAT * 16;
+        v.off_idx = o; o += round_up(d.B, 4);
+        v.off_y = o; o += round_up(d.B * (d.kind == B2E_PROBLEM_LINREG ? d.C : 1), 4);
+        v.off_lb = o; o += round_up(d.B, 4);
+        v.off_misc = o; o += 8 + 2 * B2E_MAX_HISTORY;
+        h->smem_eval = (size_t)o * sizeof(float);
+        v.split = d.split;
+    }
     return 0;
 }
 
@@ -1736,7 +2055,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->launches = 0;
     h->dataset_bound = h->stream_bound = false;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -1770,7 +2089,8 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         return bail("b2e_create: cudaMalloc of env state failed");
     if (d.split) {
         if (!dmalloc((void **)&h->gnext, EP * 4) ||
-            !dmalloc((void **)&h->part, (size_t)d.E * d.nseg * 4 * sizeof(double)))
+            !dmalloc((void **)&h->part, (size_t)d.E * d.nseg * 4 * sizeof(double)) ||
+            !dmalloc((void **)&h->part_u, (size_t)d.E * d.nsegU * 4 * sizeof(double)))
             return bail("b2e_create: cudaMalloc of the split-path buffers failed");
         cudaMemset(h->gnext, 0, EP * 4);
         int prio_least = 0, prio_greatest = 0;
@@ -1792,8 +2112,18 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(kernel_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_eval) != cudaSuccess ||
+            cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_eval) != cudaSuccess)
+            return bail("b2e_create: eval kernel does not fit shared memory");
+        int occ_ev = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, eval_kernel<true>, 256, h->smem_eval) !=
+                cudaSuccess || occ_ev < 1)
+            return bail("b2e_create: eval kernel does not fit an SM");
+        h->eval_grid = occ_ev * h->num_sms;
         h->chunk_envs = 4 * h->num_sms;
-        h->obs_grid = 2 * h->num_sms;
+        h->obs_grid = 1 << 30;
     }
     cudaMemset(h->w, 0, EP * 4); cudaMemset(h->gprev, 0, EP * 4);
     cudaMemset(h->ringw, 0, EP * d.H * 4); cudaMemset(h->ringg, 0, EP * d.H * 4);
@@ -1829,7 +2159,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (!ok) return bail("b2e_create: row table: " + err);
     }
     d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
-    d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part;
+    d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part; d.part_u = h->part_u;
     d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
     d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param; d.param_of_row = h->param_of_row;
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
@@ -1842,7 +2172,7 @@ void b2e_destroy(b2e_handle h) {
     if (!h) return;
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
-    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part);
+    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1921,49 +2251,28 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     a.mode = MODE_STEP; a.actions = actions; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
     a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out;
     if (!h->d.split) return launch(h, a, stream);
-    // ---- split path: per chunk of envs, compute kernel on the caller's stream and the
-    // streaming observation kernel on the side stream, so chunk c's observations are
-    // written while chunk c+1 is being computed
+    // ---- large problems: eval(w) -> update -> eval(w') -> observations, all on the caller's stream
     cudaStream_t main_s = (cudaStream_t)stream;
     Dev &d = h->d;
-    CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_s));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    CUDA_TRY(h, cudaStreamWaitEvent(h->hi, h->ev_fork, 0));
-    int chunk = 0;
-    static const bool trace = getenv("B2E_TRACE") != nullptr;      // debug: per-kernel timeline
-    cudaEvent_t tr[4][16];
-    if (trace) for (auto &row : tr) for (auto &ev : row) cudaEventCreate(&ev);
-    if (trace) cudaEventRecord(tr[0][15], h->hi);
-    for (int e0 = 0; e0 < d.E; e0 += h->chunk_envs, ++chunk) {
-        const int ec = d.E - e0 < h->chunk_envs ? d.E - e0 : h->chunk_envs;
-        StepArgs ac = a;
-        ac.e_begin = e0; ac.e_count = ec;
-        if (trace && chunk < 15) cudaEventRecord(tr[0][chunk], h->hi);
-        if (launch(h, ac, h->hi)) return 1;
-        if (trace && chunk < 15) cudaEventRecord(tr[1][chunk], h->hi);
-        cudaEvent_t ev = h->ev_chunk[chunk & 63];
-        CUDA_TRY(h, cudaEventRecord(ev, h->hi));
-        CUDA_TRY(h, cudaStreamWaitEvent(h->side, ev, 0));
-        const int items = d.nseg * ec;
-        const int grid = items < h->obs_grid ? items : h->obs_grid;
-        if (trace && chunk < 15) cudaEventRecord(tr[2][chunk], h->side);
-        if (d.H == 5) obs_kernel<5><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
-        else obs_kernel<0><<<grid, OBS_WARPS * 32, h->smem_obs, h->side>>>(d, ac);
-        if (trace && chunk < 15) cudaEventRecord(tr[3][chunk], h->side);
-        h->launches++;
-        CUDA_TRY(h, cudaGetLastError());
+    {
+        Dev &v = h->d_eval;                                  // same pointers, eval-kernel smem layout
+        v.gprev = d.gprev; v.gnext = d.gnext; v.perm_stride = d.perm_stride;
+        v.X = d.X; v.labels = d.labels; v.targets = d.targets; v.w = d.w; v.sc = d.sc;
+        v.ord = d.ord; v.perm = d.perm; v.part = d.part; v.part_u = d.part_u;
+        v.ringw = d.ringw; v.ringg = d.ringg; v.row_of_param = d.row_of_param; v.param_of_row = d.param_of_row;
     }
-    if (trace) {
-        cudaDeviceSynchronize();
-        for (int c = 0; c < chunk && c < 15; ++c) {
-            float t[4];
-            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tr[0][15], tr[k][c]);
-            fprintf(stderr, "chunk %d: compute %.3f..%.3f ms   observe %.3f..%.3f ms\n", c, t[0], t[1], t[2], t[3]);
-        }
-        for (auto &row : tr) for (auto &ev : row) cudaEventDestroy(ev);
+    a.e_begin = 0; a.e_count = d.E;
+    const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
+    eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
+    eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    {
+        const int items = d.nseg * d.E;
+        if (d.H == 5) obs_kernel<5><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
+        else obs_kernel<0><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
     }
-    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->side));
-    CUDA_TRY(h, cudaStreamWaitEvent(main_s, h->ev_join, 0));
+    h->launches += 4;
+    CUDA_TRY(h, cudaGetLastError());
     info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
