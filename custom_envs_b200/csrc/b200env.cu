@@ -1250,121 +1250,127 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_consta
     __shared__ double red[OBS_WARPS * 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = HT > 0 ? HT : d.H, OD = d.OD;
-    float *obsL = sm;                                         // [B2E_MAX_HISTORY]
+    constexpr int HB = HT > 0 ? HT : 1;
+    float *obsL_s = sm;                                       // [B2E_MAX_HISTORY]
     float *stage = sm + B2E_MAX_HISTORY + warp * (32 * OD + 8);
-    // persistent CTAs: a fixed number per SM so that the compute kernel always finds room
     const int nitems = a.e_count * d.nseg;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int e = a.e_begin + item / d.nseg;
-    const int seg = item - (item / d.nseg) * d.nseg;
-    const EnvScalars *sc = d.sc + e;
-    const int head = sc->head, nvalid = sc->nvalid;          // already advanced by the compute kernel
-    __syncthreads();
-    if (threadIdx.x < H) {
-        const int h = threadIdx.x;
-        float v = 0.f;
-        if (h < nvalid) {
-            int slot = head - h;
-            slot += slot < 0 ? H : 0;
-            v = sc->adj_loss[slot];
+        const int eo = item / d.nseg;
+        const int e = a.e_begin + eo;
+        const int seg = item - eo * d.nseg;
+        const EnvScalars *sc = d.sc + e;
+        const int head = sc->head, nvalid = sc->nvalid;      // already advanced by the second eval
+        __syncthreads();
+        if (threadIdx.x < H) {
+            const int h = threadIdx.x;
+            float v = 0.f;
+            if (h < nvalid) {
+                int slot = head - h;
+                slot += slot < 0 ? H : 0;
+                v = sc->adj_loss[slot];
+            }
+            obsL_s[h] = clip_m1(v);
         }
-        obsL[h] = clip_m1(v);
-    }
-    __syncthreads();
-    const float *gnew = d.gnext + (size_t)e * d.Pp;
-    const float *gold = d.gprev + (size_t)e * d.Pp;
-    const float *rw = d.ringw + (size_t)e * H * d.Pp;
-    float *rg = d.ringg + (size_t)e * H * d.Pp;
-    float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
-    for (int it = 0; it < OBS_ITERS; ++it) {
-        const int rbase = seg * SEG_ROWS + (it * OBS_WARPS + warp) * 32;
-        if (rbase >= d.P) break;
-        const int r = rbase + lane;
-        const bool ok = r < d.P;
-        const int p = ok ? (d.row_lex ? d.param_of_row[r] : r) : 0;
-        constexpr int HB = HT > 0 ? HT : 1;
-        float wv[HB], gv[HB];
-        const float g = gnew[p], gp = gold[p];
+        __syncthreads();
+        const float *gnew = d.gnext + (size_t)e * d.Pp;
+        const float *gold = d.gprev + (size_t)e * d.Pp;
+        const float *rw = d.ringw + (size_t)e * H * d.Pp;
+        float *rg = d.ringg + (size_t)e * H * d.Pp;
+        float *rg_new = rg + (size_t)head * d.Pp;
+        float *obs_env = a.obs + (size_t)e * d.P * OD;
+        // per-history-slot base pointers and loss columns (uniform across the CTA)
+        const float *rwh[HB], *rgh[HB];
+        float ol[HB];
         if (HT > 0) {
 #pragma unroll
             for (int h = 0; h < HB; ++h) {
-                wv[h] = 0.f; gv[h] = 0.f;
-                if (h < nvalid) {
-                    int slot = head - h;
-                    slot += slot < 0 ? HB : 0;
-                    wv[h] = rw[(size_t)slot * d.Pp + p];
-                    if (h > 0) gv[h] = rg[(size_t)slot * d.Pp + p];
-                }
+                int slot = head - h;
+                slot += slot < 0 ? HB : 0;
+                rwh[h] = rw + (size_t)slot * d.Pp;
+                rgh[h] = rg + (size_t)slot * d.Pp;
+                ol[h] = obsL_s[h];
             }
         }
-        const float ag = ratio_nn(g, gp);                         // utils_env.py:156-157
-        float *srow = stage + 4 + lane * OD;
-        if (ok) {
-            rg[(size_t)head * d.Pp + p] = ag;
-            s_absadjg += fabsf(ag);
-            s_gdiff += fabsf(g - gp);
-        }
-        if (HT > 0) {
-            gv[0] = ag;
+        float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
+        for (int it = 0; it < OBS_ITERS; ++it) {
+            const int rbase = seg * SEG_ROWS + (it * OBS_WARPS + warp) * 32;
+            if (rbase >= d.P) break;
+            const int r = rbase + lane;
+            const bool ok = r < d.P;
+            const int p = ok ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+            const float g = gnew[p], gp = gold[p];
+            float wv[HB], gv[HB];
+            if (HT > 0) {
 #pragma unroll
-            for (int h = 0; h < HB; ++h) {
-                if (ok) s_state += fabsf(wv[h]) + fabsf(gv[h]);
-                srow[h] = clip_only_m1(wv[h]);
-                srow[HB + h] = obsL[h];
-                srow[2 * HB + h] = clip_only_m1(gv[h]);
-            }
-        } else {
-            for (int h = 0; h < H; ++h) {
-                float w1 = 0.f, g1 = 0.f;
-                if (h < nvalid) {
-                    int slot = head - h;
-                    slot += slot < 0 ? H : 0;
-                    w1 = rw[(size_t)slot * d.Pp + p];
-                    g1 = h > 0 ? rg[(size_t)slot * d.Pp + p] : ag;
+                for (int h = 0; h < HB; ++h) {
+                    wv[h] = 0.f; gv[h] = 0.f;
+                    if (h < nvalid) {
+                        wv[h] = rwh[h][p];
+                        if (h > 0) gv[h] = rgh[h][p];
+                    }
                 }
-                if (ok) s_state += fabsf(w1) + fabsf(g1);
-                srow[h] = clip_only_m1(w1);
-                srow[H + h] = obsL[h];
-                srow[2 * H + h] = clip_only_m1(g1);
+            }
+            // stage so that shared and global memory share their 16-byte phase
+            const unsigned w_lo = (unsigned)rbase * OD;           // word offset inside this env's block
+            const unsigned sh = (unsigned)((((size_t)e * d.P * OD) + w_lo) & 3);
+            float *srow = stage + sh + lane * OD;
+            const float ag = ratio_nn(g, gp);                     // utils_env.py:156-157
+            if (ok) {
+                rg_new[p] = ag;
+                s_absadjg += fabsf(ag);
+                s_gdiff += fabsf(g - gp);
+            }
+            if (HT > 0) {
+                gv[0] = ag;
+#pragma unroll
+                for (int h = 0; h < HB; ++h) {
+                    if (ok) s_state += fabsf(wv[h]) + fabsf(gv[h]);
+                    srow[h] = clip_only_m1(wv[h]);
+                    srow[HB + h] = ol[h];
+                    srow[2 * HB + h] = clip_only_m1(gv[h]);
+                }
+            } else {
+                for (int h = 0; h < H; ++h) {
+                    float w1 = 0.f, g1 = 0.f;
+                    if (h < nvalid) {
+                        int slot = head - h;
+                        slot += slot < 0 ? H : 0;
+                        w1 = rw[(size_t)slot * d.Pp + p];
+                        g1 = h > 0 ? rg[(size_t)slot * d.Pp + p] : ag;
+                    }
+                    if (ok) s_state += fabsf(w1) + fabsf(g1);
+                    srow[h] = clip_only_m1(w1);
+                    srow[H + h] = obsL_s[h];
+                    srow[2 * H + h] = clip_only_m1(g1);
+                }
+            }
+            __syncwarp();
+            // contiguous write of this warp's rows: words [0, nw) of `dst`, stage word i at stage[sh + i]
+            const unsigned nw = (unsigned)min(32, d.P - rbase) * OD;
+            float *dst = obs_env + w_lo;
+            const float *src = stage + sh;
+            const unsigned head_w = min(nw, (4u - sh) & 3u);      // scalars up to the first aligned word
+            const unsigned body_e = head_w + ((nw - head_w) & ~3u);
+            if (lane < head_w) dst[lane] = src[lane];
+            for (unsigned i = head_w + lane * 4; i < body_e; i += 128)
+                *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
+            if (body_e + lane < nw) dst[body_e + lane] = src[body_e + lane];
+            __syncwarp();
+        }
+        // per-segment partials (deterministic: fixed order inside the CTA, summed per env later)
+        const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+        const double v2 = warp_sum((double)s_state);
+        if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double *out = d.part + ((size_t)e * d.nseg + seg) * 4;
+            for (int i = 0; i < 3; ++i) {
+                double v = 0.0;
+                for (int w = 0; w < OBS_WARPS; ++w) v += red[w * 4 + i];
+                out[i] = v;
             }
         }
-        __syncwarp();
-        // contiguous write of this warp's rows: [g_lo, g_hi) words of the obs tensor
-        const int nrows = min(32, d.P - rbase);
-        const size_t g_lo = ((size_t)e * d.P + rbase) * OD, g_hi = g_lo + (size_t)nrows * OD;
-        const int sh = (int)(g_lo & 3);                           // smem index = x - g_lo + 4
-        // stage + 4 holds word g_lo; 16-byte phase of smem (stage is 16B aligned, +4 words) is 0,
-        // of global it is sh: copy head words scalar, then aligned float4 with an smem shift
-        size_t b_lo = (g_lo + 3) & ~(size_t)3, b_hi = g_hi & ~(size_t)3;
-        if (b_lo >= b_hi) { b_lo = g_hi; b_hi = g_hi; }
-        const float *src = stage + 4;
-        for (size_t x = g_lo + lane; x < b_lo; x += 32) a.obs[x] = src[x - g_lo];
-        if (sh == 0) {
-            for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128)
-                *reinterpret_cast<float4 *>(a.obs + x) = *reinterpret_cast<const float4 *>(src + (x - g_lo));
-        } else {
-            for (size_t x = b_lo + (size_t)lane * 4; x < b_hi; x += 128) {
-                const float *q = src + (x - g_lo);
-                *reinterpret_cast<float4 *>(a.obs + x) = make_float4(q[0], q[1], q[2], q[3]);
-            }
-        }
-        for (size_t x = b_hi + lane; x < g_hi; x += 32) a.obs[x] = src[x - g_lo];
-        __syncwarp();
     }
-    // per-segment partials (deterministic: fixed order inside the CTA, summed per env later)
-    const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
-    const double v2 = warp_sum((double)s_state);
-    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double *out = d.part + ((size_t)e * d.nseg + seg) * 4;
-        for (int i = 0; i < 3; ++i) {
-            double v = 0.0;
-            for (int w = 0; w < OBS_WARPS; ++w) v += red[w * 4 + i];
-            out[i] = v;
-        }
-    }
-    }   // item loop
 }
 
 // =========================================================================================

@@ -46,7 +46,7 @@ def main():
     hdr = rows[hdr_i]
     col = {name: hdr.index(name) for name in ('Source', '# Samples', 'Instructions Executed',
                                              'L1 Wavefronts Shared', 'L2 Theoretical Sectors Global')}
-    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr) and r[0] != 'Address']
     lines = sass_lines(so_path, kernel)
     if len(lines) != len(body):
         print('warning: %d SASS rows in the report vs %d in the library' % (len(body), len(lines)))
