@@ -7,7 +7,8 @@
 Workload (N=1): BASELINE.json configs[3], the configuration the headline target is quoted
 on: MultiOptLRs, 2-layer MLP 784->64->10 on synthetic MNIST-shaped data (60000 rows),
 minibatch 32, max_history 5, 4096 lock-step envs per GPU (weak scaling: 4096 x N envs).
-One "step" = one batched env step = one launch of the fused kernel over all envs.
+One "step" = one batched env step over all envs = one b2e_step call (for this workload a
+pipeline of four kernels: eval, update, eval, observations + two tiny bookkeeping launches).
 
 Reported on one JSON line:
   value     env-steps/s with actions already in HBM (device API, CUDA events, max over ranks)
@@ -152,7 +153,7 @@ def reference_arm(args):
         return
     cores = os.cpu_count() or 1
     threads = min(cores, 32)
-    envs_per_thread = 2
+    envs_per_thread = 8
     value, elapsed = cpu_env_steps_per_s(envs_per_thread, threads, args.steps, args.warmup)
     sample = '%d envs (%d threads x %d) x %d steps of the workload, oracle numpy float32' % (
         envs_per_thread * threads, threads, envs_per_thread, args.steps)
@@ -249,18 +250,41 @@ def gpu_arm(args):
     h2d = host_actions.nbytes
     d2h = states.nbytes + env.reward.numel() * 4 + env.done.numel() + env.info.numel() * 8
 
-    # NCCL is used only for statistics: all-gather the per-env episode reward of the last step
+    # per-kernel durations of the step pipeline (CUDA events recorded inside the library,
+    # on the stream the kernels are launched on), averaged over a few extra traced steps
+    env.set_trace(True)
+    kernel_ms = {}
+    traced = 5
+    for i in range(traced):
+        env.step(actions[i & 1])
+        for name, ms_k in env.last_step_kernel_ms().items():
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + ms_k / traced
+    env.set_trace(False)
+
+    # NCCL is used only for statistics: all-gather per-env episode statistics
     if world > 1:
-        gathered = [torch.empty_like(env.reward) for _ in range(world)]
-        dist.all_gather(gathered, env.reward)
+        from custom_envs_b200.sharding import gather_env_stats
+        gather_env_stats(torch.stack([env.reward, env.info[:, 15].float()], dim=1))
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        # algorithmic bytes of each pipeline kernel per env-step (fp32 words per parameter):
+        #   eval: read w (P) + minibatch B*(D+1), write g (P)                        x2
+        #   update: read w, g0, action (3P); write w, adj_w (2P)
+        #   obs: read g_t, g_prev, 2(H-1) ring slots; write adj_g, 3H observation words
+        words = {'eval_kernel<w_prev>': 2 * NUM_PARAMS + BATCH * (D + 1),
+                 'update_kernel': 5 * NUM_PARAMS,
+                 'eval_kernel<w_new>': 2 * NUM_PARAMS + BATCH * (D + 1),
+                 'obs_kernel': (2 + 2 * (HIST - 1) + 1 + 3 * HIST) * NUM_PARAMS}
+        kernels = [{'name': k, 'ms': v, 'bytes': 4 * words[k] * envs,
+                    'gbs': 4 * words[k] * envs / (v * 1e-3) / 1e9} for k, v in kernel_ms.items()]
+        dominant = max(kernels, key=lambda k: k['ms']) if kernels else None
         launch_ms = ms / args.steps
-        achieved = BYTES_PER_ENV_STEP * envs / (launch_ms * 1e-3) / 1e9
+        step_gbs = BYTES_PER_ENV_STEP * envs / (launch_ms * 1e-3) / 1e9
+        achieved = dominant['gbs'] if dominant else step_gbs
         cores = os.cpu_count() or 1
         threads = min(cores, 32)
-        cpu_value, cpu_elapsed = cpu_env_steps_per_s(2, threads, 3, 1)
+        cpu_value, cpu_elapsed = cpu_env_steps_per_s(8, threads, 20, 1)
         line = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
@@ -279,11 +303,15 @@ def gpu_arm(args):
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
-                         'kernel': 'optenv_kernel (1 launch per step)',
-                         'bytes_per_launch': BYTES_PER_ENV_STEP * envs},
+                         'kernel': dominant['name'] if dominant else 'optenv_kernel',
+                         'bytes_per_launch': dominant['bytes'] if dominant else BYTES_PER_ENV_STEP * envs,
+                         'kernels': kernels,
+                         'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
+                                        'bytes_per_step': BYTES_PER_ENV_STEP * envs,
+                                        'note': 'SURVEY 8d algorithmic bytes of the fused step / step time'}},
             'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d envs x 3 steps of the workload (oracle numpy float32, '
-                                       '%d threads), %.1f s' % (2 * threads, threads, cpu_elapsed)},
+                             'sample': '%d envs x 20 steps of the workload (oracle numpy float32, '
+                                       '%d threads), %.1f s' % (8 * threads, threads, cpu_elapsed)},
         }
         print(json.dumps(line), flush=True)
     env.close()

@@ -22,7 +22,7 @@ EXPORTS = (
     'b2e_abi_version', 'b2e_create', 'b2e_destroy', 'b2e_last_error', 'b2e_num_params',
     'b2e_obs_dim', 'b2e_bind_dataset', 'b2e_set_index_stream', 'b2e_reset', 'b2e_step',
     'b2e_eval', 'b2e_get_state', 'b2e_set_state', 'b2e_get_batch_indices', 'b2e_next_batch',
-    'b2e_launch_count')
+    'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count')
 
 
 class Config(ctypes.Structure):
@@ -68,6 +68,8 @@ def load():
     lib.b2e_set_state.argtypes = [vp, i32, vp, usize, vp]
     lib.b2e_get_batch_indices.argtypes = [vp, vp, vp, vp]
     lib.b2e_next_batch.argtypes = [vp, vp, vp]
+    lib.b2e_set_trace.argtypes = [vp, i32]
+    lib.b2e_get_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32]
     lib.b2e_launch_count.argtypes = [vp]
     lib.b2e_launch_count.restype = ctypes.c_int64
     if lib.b2e_abi_version() != 1:

@@ -256,6 +256,17 @@ class BatchedOptEnv:
             mask = torch.as_tensor(env_mask).to(self.device, torch.uint8).contiguous()
         self._check(self.lib.b2e_next_batch(self.handle, _ptr(mask), self._stream()))
 
+    PIPELINE_KERNELS = ('eval_kernel<w_prev>', 'update_kernel', 'eval_kernel<w_new>', 'obs_kernel')
+
+    def set_trace(self, enabled=True):
+        self._check(self.lib.b2e_set_trace(self.handle, int(enabled)))
+
+    def last_step_kernel_ms(self):
+        """Per-kernel durations of the last traced step ({} for the single-kernel path)."""
+        buf = (ctypes.c_float * 8)()
+        n = self.lib.b2e_get_trace(self.handle, buf, 8)
+        return {name: float(buf[i]) for i, name in enumerate(self.PIPELINE_KERNELS[:max(n, 0)])}
+
     def info_dict(self, info=None):
         """info [E,16] -> {key: np.ndarray[E]} with the reference's key names."""
         arr = (self.info if info is None else info).cpu().numpy()

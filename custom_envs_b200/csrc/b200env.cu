@@ -1832,6 +1832,9 @@ struct b2e_env {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t ev_chunk[64];
     bool dataset_bound, stream_bound;
+    bool trace;                      // record per-kernel events in b2e_step
+    cudaEvent_t tr[8];
+    int tr_count;
     int64_t launches;
     std::string error;
 };
@@ -2060,6 +2063,8 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->cfg = *cfg;
     h->launches = 0;
     h->dataset_bound = h->stream_bound = false;
+    h->trace = false; h->tr_count = 0;
+    for (auto &ev : h->tr) ev = nullptr;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
@@ -2184,6 +2189,7 @@ void b2e_destroy(b2e_handle h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto &ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->tr) if (ev) cudaEventDestroy(ev);
     delete h;
 }
 
@@ -2269,14 +2275,21 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     }
     a.e_begin = 0; a.e_count = d.E;
     const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
+    auto mark = [&](int i) { if (h->trace) cudaEventRecord(h->tr[i], main_s); };
+    mark(0);
     eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    mark(1);
     update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
+    mark(2);
     eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    mark(3);
     {
         const int items = d.nseg * d.E;
         if (d.H == 5) obs_kernel<5><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
         else obs_kernel<0><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
     }
+    mark(4);
+    h->tr_count = h->trace ? 4 : 0;
     h->launches += 4;
     CUDA_TRY(h, cudaGetLastError());
     info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
@@ -2362,6 +2375,26 @@ int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
+}
+
+int b2e_set_trace(b2e_handle h, int enabled) {
+    if (!h) return 1;
+    if (enabled)
+        for (auto &ev : h->tr)
+            if (!ev && cudaEventCreate(&ev) != cudaSuccess) return fail(h, "b2e_set_trace: cudaEventCreate failed");
+    h->trace = enabled != 0;
+    h->tr_count = 0;
+    return 0;
+}
+
+int b2e_get_trace(b2e_handle h, float *ms_out, int capacity) {
+    if (!h || !ms_out) return -1;
+    int n = h->tr_count < capacity ? h->tr_count : capacity;
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventSynchronize(h->tr[i + 1]) != cudaSuccess ||
+            cudaEventElapsedTime(&ms_out[i], h->tr[i], h->tr[i + 1]) != cudaSuccess) return -1;
+    }
+    return n;
 }
 
 int b2e_next_batch(b2e_handle h, const uint8_t *env_mask, void *stream) {

@@ -140,6 +140,13 @@ int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void
  * NULL = all): advance to the next minibatch, reshuffling at the end of an epoch. */
 int b2e_next_batch(b2e_handle h, const uint8_t *env_mask, void *stream);
 
+/* Per-kernel timing of the large-problem step pipeline (bench bookkeeping, off by default):
+ * with tracing enabled b2e_step records a CUDA event between its kernels; b2e_get_trace
+ * synchronises on them and returns how many durations (ms) it wrote, in launch order:
+ * eval(w_{t-1}), update, eval(w_t), observations.  Returns 0 for the single-kernel path. */
+int b2e_set_trace(b2e_handle h, int enabled);
+int b2e_get_trace(b2e_handle h, float *ms_out, int capacity);
+
 /* Kernel launches issued on behalf of this handle so far (bench bookkeeping). */
 int64_t b2e_launch_count(b2e_handle h);
 
