@@ -71,13 +71,17 @@ class ClockSampler:
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """The timed region starts now: earlier samples are dropped."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -94,7 +98,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 9:
                 continue
@@ -207,12 +211,17 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                       # nvidia-smi needs ~1 s to produce its first line
     for i in range(max(args.warmup, 3)):
         env.step(actions[i & 1])
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        deadline = time.time() + 3.0
+        while not sampler.lines and time.time() < deadline:
+            time.sleep(0.05)
+        sampler.mark()
     launches0 = env.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     done_total = 0
@@ -322,7 +331,7 @@ def gpu_arm(args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=20)
+    parser.add_argument('--steps', type=int, default=50)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     parser.add_argument('--envs', type=int, default=4096, help='envs per GPU')
