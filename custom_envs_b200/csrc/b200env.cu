@@ -1373,6 +1373,269 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) obs_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------- observation kernel, asynchronous gathers
+// Same work as obs_kernel, organised for memory-level parallelism: a WARP owns 32 units of
+// 32 consecutive agent rows of one env and runs a private S-stage pipeline over them.  The
+// 2H+1 four-byte gathers of a row (g_t, g_{t-1}, H adjusted-weight slots, H-1 adjusted-gradient
+// slots) are cp.async copies into the warp's shared-memory stage, so S units of loads are in
+// flight per warp without holding registers or scoreboard slots; no CTA-wide barrier exists.
+// The 32 finished rows (32 * 3H words, contiguous in HBM) leave either through 16-byte stores
+// or as one cp.async.bulk shared->global copy issued by lane 0.
+constexpr int O2_WARPS = 4;
+constexpr int O2_UNITS = 32;
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, unsigned bytes) {
+    const unsigned src = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 ::"l"(gmem_dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <int H, int S, bool BULK>
+__global__ void __launch_bounds__(O2_WARPS * 32) obs_kernel2(const __grid_constant__ Dev d,
+                                                             const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int OD = 3 * H, NPL = 2 * H + 1, NPL1 = NPL + 1;   // + the row's parameter index
+    constexpr int STG = 32 * OD + 8;
+    constexpr int PER_WARP = S * NPL1 * 32 + (BULK ? 2 : 1) * STG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * O2_WARPS + warp;
+    if (item >= a.e_count * d.nseg) return;                  // nseg = 32-unit chunks per env
+    float *gat = sm + warp * PER_WARP;
+    float *stage0 = gat + S * NPL1 * 32;
+    const int eo = item / d.nseg, chunk = item - eo * d.nseg;
+    const int e = a.e_begin + eo;
+    const EnvScalars *sc = d.sc + e;
+    const int head = sc->head, nvalid = sc->nvalid;          // already advanced by the second eval
+    float ol[H];
+    const float *src[NPL];
+    src[0] = d.gnext + (size_t)e * d.Pp;
+    src[1] = d.gprev + (size_t)e * d.Pp;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        int slot = head - h;
+        slot += slot < 0 ? H : 0;
+        ol[h] = clip_m1(h < nvalid ? sc->adj_loss[slot] : 0.f);
+        src[2 + h] = d.ringw + ((size_t)e * H + slot) * d.Pp;
+        if (h > 0) src[2 + H + h - 1] = d.ringg + ((size_t)e * H + slot) * d.Pp;
+    }
+    float *rg_new = d.ringg + ((size_t)e * H + head) * d.Pp;
+    float *obs_env = a.obs + (size_t)e * d.P * OD;
+    const int nblk = (d.P + 31) >> 5;
+    const int u0 = chunk * O2_UNITS;
+    const int nu = min(O2_UNITS, nblk - u0);
+    auto row_param = [&](int it) -> int {
+        const int r = (u0 + it) * 32 + lane;
+        return r < d.P ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+    };
+    auto issue = [&](int it, int p) {
+        float *dst = gat + (it % S) * (NPL1 * 32) + lane;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int h = k < 2 ? 0 : (k < 2 + H ? k - 2 : k - 1 - H);
+            if (h < nvalid) cp_async4(dst + k * 32, src[k] + p);
+        }
+        reinterpret_cast<int *>(dst)[NPL * 32] = p;
+    };
+#pragma unroll
+    for (int it = 0; it < S; ++it) {
+        if (it < nu) issue(it, row_param(it));
+        cp_async_commit();
+    }
+    int p_next = S < nu ? row_param(S) : 0;
+    float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
+    for (int it = 0; it < nu; ++it) {
+        cp_async_wait<S - 1>();
+        const float *gs = gat + (it % S) * (NPL1 * 32) + lane;
+        const float g = gs[0], gp = gs[32];
+        const int p = reinterpret_cast<const int *>(gs)[NPL * 32];
+        float wv[H], gv[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            wv[h] = h < nvalid ? gs[(2 + h) * 32] : 0.f;
+            gv[h] = (h > 0 && h < nvalid) ? gs[(2 + H + h - 1) * 32] : 0.f;
+        }
+        if (it + S < nu) issue(it + S, p_next);              // refill the stage just consumed
+        cp_async_commit();
+        if (it + S + 1 < nu) p_next = row_param(it + S + 1);
+        const int rbase = (u0 + it) * 32;
+        const bool ok = rbase + lane < d.P;
+        const float ag = ratio_nn(g, gp);                    // utils_env.py:156-157
+        if (ok) {
+            rg_new[p] = ag;
+            s_absadjg += fabsf(ag);
+            s_gdiff += fabsf(g - gp);
+        }
+        gv[0] = ag;
+        // stage so that shared and global memory share their 16-byte phase
+        const unsigned w_lo = (unsigned)rbase * OD;
+        const unsigned sh = (unsigned)((((size_t)e * d.P * OD) + w_lo) & 3);
+        float *stage = stage0 + (BULK ? (it & 1) * STG : 0);
+        if (BULK) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+            __syncwarp();
+        }
+        float *srow = stage + sh + lane * OD;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            if (ok) s_state += fabsf(wv[h]) + fabsf(gv[h]);
+            srow[h] = clip_only_m1(wv[h]);
+            srow[H + h] = ol[h];
+            srow[2 * H + h] = clip_only_m1(gv[h]);
+        }
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        const unsigned nw = (unsigned)min(32, d.P - rbase) * OD;
+        float *dst = obs_env + w_lo;
+        const float *srcw = stage + sh;
+        const unsigned head_w = min(nw, (4u - sh) & 3u);     // scalars up to the first aligned word
+        const unsigned body_e = head_w + ((nw - head_w) & ~3u);
+        if (lane < head_w) dst[lane] = srcw[lane];
+        if (BULK) {
+            if (lane == 0) {
+                if (body_e > head_w) bulk_store(dst + head_w, srcw + head_w, (body_e - head_w) * 4u);
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
+        } else {
+            for (unsigned i = head_w + lane * 4; i < body_e; i += 128)
+                *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(srcw + i);
+        }
+        if (body_e + lane < nw) dst[body_e + lane] = srcw[body_e + lane];
+        if (!BULK) __syncwarp();
+    }
+    if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+    const double v2 = warp_sum((double)s_state);
+    if (lane == 0) {
+        double *out = d.part + ((size_t)e * d.nseg + chunk) * 4;
+        out[0] = v0; out[1] = v1; out[2] = v2;
+    }
+}
+
+// ------------------------------------------- observation kernel, register-batched gathers
+// As obs_kernel2, but the loads stay in registers: every lane issues the 2H+1 gathers of R
+// rows (R units of 32 rows per warp iteration) back to back before the first use, so a warp
+// has R*(2H+1) loads in flight at the LSU cost of plain LDG.
+template <int H, int R, bool BULK>
+__global__ void __launch_bounds__(O2_WARPS * 32) obs_kernel3(const __grid_constant__ Dev d,
+                                                             const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int OD = 3 * H;
+    constexpr int STG = 32 * OD + 8;
+    constexpr int PER_WARP = (BULK ? 2 : 1) * STG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * O2_WARPS + warp;
+    if (item >= a.e_count * d.nseg) return;
+    float *stage0 = sm + warp * PER_WARP;
+    const int eo = item / d.nseg, chunk = item - eo * d.nseg;
+    const int e = a.e_begin + eo;
+    const EnvScalars *sc = d.sc + e;
+    const int head = sc->head, nvalid = sc->nvalid;
+    float ol[H];
+    const float *rwh[H], *rgh[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        int slot = head - h;
+        slot += slot < 0 ? H : 0;
+        ol[h] = clip_m1(h < nvalid ? sc->adj_loss[slot] : 0.f);
+        rwh[h] = d.ringw + ((size_t)e * H + slot) * d.Pp;
+        rgh[h] = d.ringg + ((size_t)e * H + slot) * d.Pp;
+    }
+    const float *gnew = d.gnext + (size_t)e * d.Pp;
+    const float *gold = d.gprev + (size_t)e * d.Pp;
+    float *rg_new = d.ringg + ((size_t)e * H + head) * d.Pp;
+    float *obs_env = a.obs + (size_t)e * d.P * OD;
+    const int nblk = (d.P + 31) >> 5;
+    const int u0 = chunk * O2_UNITS;
+    const int nu = min(O2_UNITS, nblk - u0);
+    float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
+    int pn[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int r = (u0 + j) * 32 + lane;
+        pn[j] = (j < nu && r < d.P) ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+    }
+    int nstore = 0;
+    for (int it = 0; it < nu; it += R) {
+        int p[R];
+        float g[R], gp[R], wv[R][H], gv[R][H];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            p[j] = pn[j];
+            g[j] = gnew[p[j]];
+            gp[j] = gold[p[j]];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                wv[j][h] = h < nvalid ? rwh[h][p[j]] : 0.f;
+                gv[j][h] = (h > 0 && h < nvalid) ? rgh[h][p[j]] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {                        // row indices of the next iteration
+            const int r = (u0 + it + R + j) * 32 + lane;
+            pn[j] = (it + R + j < nu && r < d.P) ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (it + j >= nu) break;
+            const int rbase = (u0 + it + j) * 32;
+            const bool ok = rbase + lane < d.P;
+            const float ag = ratio_nn(g[j], gp[j]);          // utils_env.py:156-157
+            if (ok) {
+                rg_new[p[j]] = ag;
+                s_absadjg += fabsf(ag);
+                s_gdiff += fabsf(g[j] - gp[j]);
+            }
+            gv[j][0] = ag;
+            const unsigned w_lo = (unsigned)rbase * OD;
+            const unsigned sh = (unsigned)((((size_t)e * d.P * OD) + w_lo) & 3);
+            float *stage = stage0 + (BULK ? (nstore & 1) * STG : 0);
+            ++nstore;
+            if (BULK) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+                __syncwarp();
+            }
+            float *srow = stage + sh + lane * OD;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                if (ok) s_state += fabsf(wv[j][h]) + fabsf(gv[j][h]);
+                srow[h] = clip_only_m1(wv[j][h]);
+                srow[H + h] = ol[h];
+                srow[2 * H + h] = clip_only_m1(gv[j][h]);
+            }
+            if (BULK) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+            const unsigned nw = (unsigned)min(32, d.P - rbase) * OD;
+            float *dst = obs_env + w_lo;
+            const float *srcw = stage + sh;
+            const unsigned head_w = min(nw, (4u - sh) & 3u);
+            const unsigned body_e = head_w + ((nw - head_w) & ~3u);
+            if (lane < head_w) dst[lane] = srcw[lane];
+            if (BULK) {
+                if (lane == 0) {
+                    if (body_e > head_w) bulk_store(dst + head_w, srcw + head_w, (body_e - head_w) * 4u);
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                }
+            } else {
+                for (unsigned i = head_w + lane * 4; i < body_e; i += 128)
+                    *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(srcw + i);
+            }
+            if (body_e + lane < nw) dst[body_e + lane] = srcw[body_e + lane];
+            if (!BULK) __syncwarp();
+        }
+    }
+    if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+    const double v2 = warp_sum((double)s_state);
+    if (lane == 0) {
+        double *out = d.part + ((size_t)e * d.nseg + chunk) * 4;
+        out[0] = v0; out[1] = v1; out[2] = v2;
+    }
+}
+
 // =========================================================================================
 // Large problems: the step is a pipeline of four kernels on the caller's stream
 //   eval_kernel<false> : g0 = grad(batch, w_{t-1})                      (2 CTAs/SM, FFMA bound)
@@ -1823,6 +2086,8 @@ struct b2e_env {
     EnvScalars *sc;
     size_t smem_obs;
     int chunk_envs, obs_grid;
+    int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
+    size_t smem_obs2;
     Dev d_eval;                      // Dev with the eval kernel's shared-memory layout
     size_t smem_eval;
     int eval_grid;
@@ -1882,6 +2147,27 @@ std::string lex_rows(int num_params, int *row_of_param_host) {
     }
     delete[] stack;
     return next_row == num_params ? "" : "internal error in lexicographic row table";
+}
+
+const void *obs2_fn(int stages, int regs, int bulk) {
+    if (regs) {
+        switch (regs * 2 + (bulk ? 1 : 0)) {
+            case 2: return (const void *)obs_kernel3<5, 1, false>;
+            case 3: return (const void *)obs_kernel3<5, 1, true>;
+            case 4: return (const void *)obs_kernel3<5, 2, false>;
+            case 5: return (const void *)obs_kernel3<5, 2, true>;
+            case 8: return (const void *)obs_kernel3<5, 4, false>;
+            default: return (const void *)obs_kernel3<5, 4, true>;
+        }
+    }
+    switch (stages * 2 + (bulk ? 1 : 0)) {
+        case 6: return (const void *)obs_kernel2<5, 3, false>;
+        case 7: return (const void *)obs_kernel2<5, 3, true>;
+        case 8: return (const void *)obs_kernel2<5, 4, false>;
+        case 9: return (const void *)obs_kernel2<5, 4, true>;
+        case 12: return (const void *)obs_kernel2<5, 6, false>;
+        default: return (const void *)obs_kernel2<5, 6, true>;
+    }
 }
 
 int configure(b2e_handle h) {
@@ -1975,6 +2261,27 @@ int configure(b2e_handle h) {
     d.off_lb = off; off += round_up(d.B, 4);
     d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
     h->smem_bytes = (size_t)off * sizeof(float);
+    {   // observation kernel variant: B2E_OBS = "<stages><b|s>" (cp.async gathers, e.g. "4b"),
+        // "r<rows><b|s>" (register-batched gathers, e.g. "r4b"), "0" = obs_kernel;
+        // b = cp.async.bulk row-block stores, s = 16-byte stores
+        const char *v = getenv("B2E_OBS");
+        h->obs_stages = 0; h->obs_regs = 4; h->obs_bulk = 1;
+        if (v && *v) {
+            h->obs_bulk = strchr(v, 's') ? 0 : 1;
+            if (*v == 'r') { h->obs_regs = atoi(v + 1); h->obs_stages = 0; }
+            else { h->obs_stages = atoi(v); h->obs_regs = 0; }
+        }
+        if (h->obs_stages != 0 && h->obs_stages != 3 && h->obs_stages != 4 && h->obs_stages != 6)
+            return fail(h, "B2E_OBS: stages must be 0, 3, 4 or 6");
+        if (h->obs_regs != 0 && h->obs_regs != 1 && h->obs_regs != 2 && h->obs_regs != 4)
+            return fail(h, "B2E_OBS: rows per lane must be 1, 2 or 4");
+        if (d.H != 5 || !d.split) h->obs_stages = h->obs_regs = 0;
+        if (h->obs_stages || h->obs_regs) {
+            d.nseg = ((d.P + 31) / 32 + O2_UNITS - 1) / O2_UNITS;
+            const int npl1 = 2 * d.H + 2, stg = 32 * d.OD + 8;
+            h->smem_obs2 = (size_t)O2_WARPS * (h->obs_stages * npl1 * 32 + (h->obs_bulk ? 2 : 1) * stg) * sizeof(float);
+        }
+    }
     h->smem_obs = (size_t)(B2E_MAX_HISTORY + OBS_WARPS * (32 * d.OD + 8)) * sizeof(float);
     d.nsegU = (d.Pp + UPD_SEG - 1) / UPD_SEG;
     {   // eval kernel: X and W1 both streamed through double-buffered tiles
@@ -2119,6 +2426,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_obs) != cudaSuccess)
             return bail("b2e_create: observation kernel does not fit (max_history too large)");
+        if ((h->obs_stages || h->obs_regs) &&
+            cudaFuncSetAttribute(obs2_fn(h->obs_stages, h->obs_regs, h->obs_bulk), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_obs2) != cudaSuccess)
+            return bail("b2e_create: observation kernel (async gathers) does not fit shared memory");
         // kernels that share an SM must agree on its L1/shared-memory split
         cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -2285,7 +2596,13 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     mark(3);
     {
         const int items = d.nseg * d.E;
-        if (d.H == 5) obs_kernel<5><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
+        if (h->obs_stages || h->obs_regs) {
+            const int grid2 = (items + O2_WARPS - 1) / O2_WARPS;
+            const void *fn = obs2_fn(h->obs_stages, h->obs_regs, h->obs_bulk);
+            void *params[2] = {(void *)&d, (void *)&a};
+            CUDA_TRY(h, cudaLaunchKernel(fn, dim3(grid2), dim3(O2_WARPS * 32), params, h->smem_obs2, main_s));
+        }
+        else if (d.H == 5) obs_kernel<5><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
         else obs_kernel<0><<<items, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
     }
     mark(4);
