@@ -5,5 +5,6 @@ that are built on the device path."""
 from custom_envs_b200.compat import register
 
 register(id='MultiOptLRs-v0', entry_point='custom_envs_b200.envs.multioptlrs:MultiOptLRs')
+register(id='MultiOptimize-v0', entry_point='custom_envs_b200.envs.multioptimize:MultiOptimize')
 
 __version__ = '0.1.0'

@@ -15,12 +15,13 @@ ROWS_LEXICOGRAPHIC, ROWS_NATURAL = 0, 1
 INDEX_INTERNAL, INDEX_EXTERNAL = 0, 1
 INFO_STRIDE = 16
 MAX_HISTORY = 32
+MAX_LAYERS = 8
 (STATE_PARAMS, STATE_GRAD_PREV, STATE_ADJ_WEIGHTS, STATE_ADJ_GRADS, STATE_ADJ_LOSSES,
  STATE_RAW_LOSSES, STATE_RAW_GSUMS, STATE_STEP, STATE_CURSOR, STATE_ORDER) = range(10)
 
 EXPORTS = (
     'b2e_abi_version', 'b2e_create', 'b2e_destroy', 'b2e_last_error', 'b2e_num_params',
-    'b2e_obs_dim', 'b2e_bind_dataset', 'b2e_set_index_stream', 'b2e_reset', 'b2e_step',
+    'b2e_obs_dim', 'b2e_history_depth', 'b2e_bind_dataset', 'b2e_set_index_stream', 'b2e_reset', 'b2e_step',
     'b2e_eval', 'b2e_get_state', 'b2e_set_state', 'b2e_get_batch_indices', 'b2e_next_batch',
     'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count')
 
@@ -30,7 +31,8 @@ class Config(ctypes.Structure):
         'struct_size', 'device', 'env_kind', 'problem_kind', 'num_features', 'num_hidden',
         'num_outputs', 'num_rows', 'batch_size', 'num_envs', 'max_batches', 'max_history',
         'history_version', 'observation_version', 'action_version', 'reward_version',
-        'row_order', 'index_mode', 'auto_reset', 'reserved')] + [('init_seed', ctypes.c_uint64)]
+        'row_order', 'index_mode', 'auto_reset', 'reserved')] + [
+        ('hidden_more', ctypes.c_int32 * MAX_LAYERS), ('init_seed', ctypes.c_uint64)]
 
 
 class B200EnvError(RuntimeError):
@@ -59,6 +61,7 @@ def load():
     lib.b2e_last_error.restype = ctypes.c_char_p
     lib.b2e_num_params.argtypes = [vp]
     lib.b2e_obs_dim.argtypes = [vp]
+    lib.b2e_history_depth.argtypes = [vp]
     lib.b2e_bind_dataset.argtypes = [vp, vp, vp, vp]
     lib.b2e_set_index_stream.argtypes = [vp, vp, i32, vp, vp]
     lib.b2e_reset.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -72,7 +75,7 @@ def load():
     lib.b2e_get_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32]
     lib.b2e_launch_count.argtypes = [vp]
     lib.b2e_launch_count.restype = ctypes.c_int64
-    if lib.b2e_abi_version() != 1:
+    if lib.b2e_abi_version() != 2:
         raise B200EnvError('libb200env.so ABI version mismatch')
     _lib = lib
     return lib

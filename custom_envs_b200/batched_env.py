@@ -80,8 +80,8 @@ class BatchedOptEnv:
             raise _lib.B200EnvError('BatchedOptEnv needs a CUDA device (no CPU fallback)')
         self.device = torch.device(device)
         self.problem = problem
-        if len(problem.hidden) > 1:
-            raise _lib.B200EnvError('at most one hidden layer is supported by the fused kernel')
+        if len(problem.hidden) > _lib.MAX_LAYERS - 1:
+            raise _lib.B200EnvError('at most %d hidden layers' % (_lib.MAX_LAYERS - 1))
         self.num_envs = int(num_envs)
         self.index_mode = index_mode
         cfg = _lib.Config()
@@ -97,6 +97,8 @@ class BatchedOptEnv:
             batch_size = num_rows if batch_size is None else int(batch_size)
             cfg.num_features, cfg.num_outputs = problem.num_features, problem.num_outputs
             cfg.num_hidden = problem.hidden[0] if problem.hidden else 0
+            for i, width in enumerate(problem.hidden[1:]):
+                cfg.hidden_more[i] = int(width)
             cfg.num_rows, cfg.batch_size = num_rows, batch_size
             assert features.shape[1] == problem.num_features
         self.batch_size = 1 if func else batch_size
@@ -116,6 +118,7 @@ class BatchedOptEnv:
         self.handle = handle
         self.num_params = self.lib.b2e_num_params(handle)
         self.obs_dim = self.lib.b2e_obs_dim(handle)
+        self.history_depth = self.lib.b2e_history_depth(handle)
         self.num_rows = self.num_envs * self.num_params
         dev = self.device
         self.obs = torch.empty((self.num_rows, self.obs_dim), dtype=torch.float32, device=dev)
@@ -219,7 +222,7 @@ class BatchedOptEnv:
         return grad, loss
 
     def _state_shape(self, name):
-        e, p, h = self.num_envs, self.num_params, self.max_history
+        e, p, h = self.num_envs, self.num_params, self.history_depth
         return {'params': (e, p), 'grad_prev': (e, p), 'adj_weights': (e, h, p),
                 'adj_grads': (e, h, p), 'adj_losses': (e, h), 'raw_losses': (e, 5),
                 'raw_gsums': (e, 5), 'step': (e,), 'cursor': (e,),

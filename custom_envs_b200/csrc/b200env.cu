@@ -32,7 +32,7 @@ constexpr int RAW_DEPTH = 5;      // reference envs/multioptlrs.py:42
 constexpr int MAXI = 4;           // forward work items per warp
 constexpr int NSTAT = 8;
 
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_EVAL = 2 };
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_EVAL = 2, MODE_EVAL_STEP = 3, MODE_EVAL_FIRST = 4 };
 enum { PASS_U = 0, PASS_G = 1, PASS_R = 2, PASS_E = 3, PASS_S = 4 };
 enum { ST_ABSW = 0, ST_LR = 1, ST_LR2 = 2, ST_G = 3, ST_ABSADJG = 4, ST_GDIFF = 5, ST_STATE = 6 };
 
@@ -75,6 +75,17 @@ struct Dev {
     int ev_X0, ev_X1, ev_W0, ev_W1, ev_XS;   // eval kernel: streamed X / W tile buffers
     int nsegU;
     double *part_u;
+    // observation layout (utils/utils_env.py:22-44): first column of each key's block or -1
+    int col_w, col_l, col_g;
+    float *w2, *g2;                  // x_{t-2} planes of the raw History, observation version 2
+    // generic dense stack (any number of hidden layers / batch size): see gen_eval_kernel
+    int generic, nlayers;            // nlayers = Dense layers = hidden layers + 1
+    int dims[B2E_MAX_LAYERS + 1];    // widths n_0 = D, n_1.., n_nlayers = C
+    int woff[B2E_MAX_LAYERS], boff[B2E_MAX_LAYERS];   // parameter offsets of kernel / bias of layer l
+    int aoff[B2E_MAX_LAYERS + 1];    // workspace offset of the activations of layer l (0 = inputs)
+    int doff0, doff1;                // two delta buffers [B, max width]
+    float *ws;                       // per-CTA workspace
+    long long ws_stride;
 };
 
 struct StepArgs {
@@ -118,6 +129,35 @@ __device__ __forceinline__ float action_to_lr(float a, int ver) {   // utils_env
         case 1: return a * 1e-3f;
         case 2: return exp2f(a);
         default: return fmaxf((a + 1e3f) * 1e-6f, 0.0f);
+    }
+}
+__device__ __forceinline__ float action_to_delta(float a, int ver) {  // multioptimize.py:95-102
+    if (ver == 1) return a * 1e-3f;
+    const float mag = exp10f(fabsf(a) - 3.0f);
+    return a > 0.f ? mag : (a < 0.f ? -mag : 0.f);
+}
+// adjusted weight / gradient / loss per observation version (utils/utils_env.py:126-164);
+// x0 newest, x1, x2 the two entries before it in the raw History
+__device__ __forceinline__ float adjust_w(int ver, float w0, float w1, float w2) {
+    switch (ver) {
+        case 2: return fabsf(w1 - w2) / (fabsf(w0 - w1) + 1e-8f);
+        case 3: return nan_to_num_f(w0 / fabsf(w1));
+        default: return w0 / (fabsf(w1) + 1e-3f);
+    }
+}
+__device__ __forceinline__ float adjust_g(int ver, float g0, float g1, float g2) {
+    switch (ver) {
+        case 1: return g0 * 1e2f;
+        case 2: return (g0 - g1) / (fabsf(g1 - g2) + 1e-3f);
+        case 3: return nan_to_num_f(g0 / fabsf(g1));
+        default: return g0 / (fabsf(g1) + 1e-3f);
+    }
+}
+__device__ __forceinline__ double adjust_l(int ver, double l0, double l1, double l2) {
+    switch (ver) {
+        case 2: return (l0 - l1) / (fabs(l1 - l2) + 1e-3);
+        case 3: return nan_to_num_d(l0 / fabs(l1));
+        default: return l0 / (fabs(l1) + 1e-3);
     }
 }
 __device__ __forceinline__ float glorot(unsigned long long seed, int e, int episode, int p,
@@ -777,6 +817,12 @@ __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCt
                 }
             }
         } else if (PASS == PASS_R || PASS == PASS_E || PASS == PASS_S) {
+            if (any && PASS == PASS_R && d.g2) {               // raw History keeps the older gradient
+                float *g2p = d.g2 + (size_t)cx.e * d.Pp + p;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (in[i]) g2p[i] = cx.gE[p + i];
+            }
             if (any) {
                 float *dst = (PASS == PASS_R) ? cx.gE + p
                            : (PASS == PASS_S) ? d.gnext + (size_t)cx.e * d.Pp + p
@@ -1008,6 +1054,7 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
             else if (d.hidden && p >= d.P1 + d.N1 && p < d.P1 + d.N1 + d.N1 * d.C)
                 v = glorot(d.seed, e, episode, p, d.lim2);
         }
+        if (d.w2) d.w2[(size_t)e * d.Pp + p] = cx.wE[p];         // raw History keeps the older weights
         cx.wE[p] = v;
     }
     __syncthreads();
@@ -1016,22 +1063,30 @@ __device__ void reset_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     const float loss = eval_current<PASS_R, BIG>(d, a, sm, cx, cnt, st);
     Totals tot;
     block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
+    const bool lrs = d.env_kind == B2E_ENV_MULTIOPTLRS;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
+        // MultiOptLRs clears its raw History (multioptlrs.py:69), MultiOptimize only the adjusted
+        // one (multioptimize.py:78-88): there the reset evaluation is one more raw entry
+        if (lrs) {
+            for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
+            sc->raw_pos = 0;
+        } else {
+            sc->raw_pos = (sc->raw_pos + 1) % RAW_DEPTH;
+        }
         for (int i = 0; i < B2E_MAX_HISTORY; ++i) sc->adj_loss[i] = 0.f;
-        sc->raw_pos = 0;
-        sc->raw_loss[0] = loss;
-        sc->raw_gsum[0] = tot.v[ST_G];
+        sc->raw_loss[sc->raw_pos] = loss;
+        sc->raw_gsum[sc->raw_pos] = tot.v[ST_G];
         sc->loss_prev = loss;
         sc->head = d.H - 1;
         sc->nvalid = 0;
         sc->step = 0;
         sc->episode = episode + 1;
     }
-    if (a.obs) {                                                  // obs = clip(0) - 1 = -1
+    if (a.obs) {                        // MultiOptLRs: clip(0) - 1 = -1; MultiOptimize: the zero history
         float *o = a.obs + (size_t)e * d.P * d.OD;
         const size_t n = (size_t)d.P * d.OD;
-        for (size_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = -1.0f;
+        const float fill = lrs ? -1.0f : 0.0f;
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = fill;
     }
     __syncthreads();
 }
@@ -1201,6 +1256,92 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     if (done && d.auto_reset && !d.split) reset_env<BIG>(d, a, sm, e);
 }
 
+// Scalar bookkeeping of one env-step once g_t and L_t are known (one thread): raw and
+// adjusted loss histories, reward, done, the scalar info entries, minibatch cursor.
+// misc[4] = 1 when the epoch wrapped (the CTA reshuffles), misc[1] = done.
+__device__ void step_scalars(const Dev &d, const StepArgs &a, EnvScalars *sc, int e, float loss,
+                             double gsum, float *misc) {
+    const bool lrs = d.env_kind == B2E_ENV_MULTIOPTLRS;
+    const int head_new = (sc->head + 1) % d.H;
+    const int nvalid_new = min(sc->nvalid + 1, d.H);
+    const double l1 = (double)sc->raw_loss[sc->raw_pos];
+    const double l2 = (double)sc->raw_loss[(sc->raw_pos + RAW_DEPTH - 1) % RAW_DEPTH];
+    const double adjl = lrs ? nan_to_num_d((double)loss / fabs((double)sc->loss_prev))
+                            : adjust_l(d.obs_ver, (double)loss, l1, l2);
+    double reward;
+    switch (d.rew_ver) {                                       // utils_env.py:71-99
+        case 0: reward = -adjl; break;
+        case 1: reward = (double)(1.0f / loss); break;
+        case 2: reward = -adjl * 100.0; break;
+        case 3: reward = (double)(1.0f / loss) * 100.0; break;
+        case 4: reward = (double)logf(1.0f / loss); break;
+        case 5: reward = -(adjl - 1.0) * (adjl - 1.0); break;
+        default: reward = -(adjl - 1.0); break;
+    }
+    const int step = sc->step + 1;                             // baseenvironment.py:37
+    bool done = step >= d.max_batches;
+    if (lrs) {
+        reward = fmin(fmax(reward, -100.0), 100.0);            // multioptlrs.py:103
+        if (!done && loss > 1e4f) {                            // multioptlrs.py:105-107
+            done = true;
+            reward -= (double)(d.max_batches - step);
+        }
+    }
+    const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
+    sc->raw_pos = rp;
+    sc->raw_loss[rp] = loss;
+    sc->raw_gsum[rp] = gsum;
+    sc->loss_prev = loss;
+    sc->adj_loss[head_new] = (float)adjl;
+    sc->head = head_new;
+    sc->nvalid = nvalid_new;
+    sc->step = step;
+    double gs = 0.0, ls = 0.0;
+    for (int i = 0; i < RAW_DEPTH; ++i) { gs += sc->raw_gsum[i]; ls += (double)sc->raw_loss[i]; }
+    double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
+    info[0] = done ? (double)loss : nan("");                   // multioptlrs.py:108-110
+    info[1] = (double)loss;
+    info[8] = gs / (RAW_DEPTH * (double)d.P);
+    info[9] = gs;
+    info[10] = ls / RAW_DEPTH;
+    info[11] = adjl;
+    info[14] = reward;                                         // baseenvironment.py:40
+    info[15] = (double)step;
+    a.reward[e] = (float)reward;
+    a.done[e] = done ? 1 : 0;
+    misc[1] = done ? 1.f : 0.f;
+    misc[4] = 0.f;
+    // MultiOptLRs moves to the next minibatch (multioptlrs.py:128); MultiOptimize never does
+    if (lrs && d.kind != B2E_PROBLEM_FUNC && d.index_mode == B2E_INDEX_INTERNAL) {
+        const int cur = sc->cursor + 1;                        // optimize_nn.py:102-112
+        misc[4] = (cur * d.B >= d.N) ? 1.f : 0.f;
+        sc->cursor = (cur * d.B >= d.N) ? 0 : cur;
+    }
+}
+
+// pipeline stage "evaluate at w_t" for problems the eval kernel does not cover: g_t to HBM,
+// then the step's scalars
+template <bool BIG>
+__device__ void eval_step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
+    EnvScalars *sc = d.sc + e;
+    EpiCtx cx;
+    make_ctx(d, e, cx);
+    const int *idx; int cnt;
+    current_batch(d, a, e, sc, idx, cnt);
+    if (d.kind != B2E_PROBLEM_FUNC) load_batch(d, sm, idx, cnt);
+    Stats st;
+    zero_stats(st);
+    const float loss = eval_current<PASS_S, BIG>(d, a, sm, cx, cnt, st);
+    Totals tot;
+    block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
+    float *misc = sm + d.off_misc;
+    if (threadIdx.x == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+    __syncthreads();
+    const bool wrap = misc[4] != 0.f;
+    __syncthreads();
+    if (wrap) shuffle_order(d, e, sc);
+}
+
 template <bool BIG>
 __device__ void eval_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     EnvScalars *sc = d.sc + e;
@@ -1226,6 +1367,8 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 2) optenv_kernel(const __grid_c
             step_env<HT, BIG>(d, a, sm, e);
         } else if (a.mode == MODE_RESET) {
             if (a.mask == nullptr || a.mask[e]) reset_env<BIG>(d, a, sm, e);
+        } else if (a.mode == MODE_EVAL_STEP) {
+            eval_step_env<BIG>(d, a, sm, e);
         } else {
             eval_env<BIG>(d, a, sm, e);
         }
@@ -1777,57 +1920,7 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
         st.f[ST_G] = gsum;
         Totals tot;
         block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
-        if (tid == 0) {
-            const int head_new = (sc->head + 1) % d.H;
-            const int nvalid_new = min(sc->nvalid + 1, d.H);
-            const double adjl = nan_to_num_d((double)loss / fabs((double)sc->loss_prev));
-            double reward;
-            switch (d.rew_ver) {                                       // utils_env.py:71-99
-                case 0: reward = -adjl; break;
-                case 1: reward = (double)(1.0f / loss); break;
-                case 2: reward = -adjl * 100.0; break;
-                case 3: reward = (double)(1.0f / loss) * 100.0; break;
-                case 4: reward = (double)logf(1.0f / loss); break;
-                case 5: reward = -(adjl - 1.0) * (adjl - 1.0); break;
-                default: reward = -(adjl - 1.0); break;
-            }
-            reward = fmin(fmax(reward, -100.0), 100.0);                // multioptlrs.py:103
-            const int step = sc->step + 1;                             // baseenvironment.py:37
-            bool done = step >= d.max_batches;
-            if (!done && loss > 1e4f) {                                // multioptlrs.py:105-107
-                done = true;
-                reward -= (double)(d.max_batches - step);
-            }
-            const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
-            sc->raw_pos = rp;
-            sc->raw_loss[rp] = loss;
-            sc->raw_gsum[rp] = tot.v[ST_G];
-            sc->loss_prev = loss;
-            sc->adj_loss[head_new] = (float)adjl;
-            sc->head = head_new;
-            sc->nvalid = nvalid_new;
-            sc->step = step;
-            double gs = 0.0, ls = 0.0;
-            for (int i = 0; i < RAW_DEPTH; ++i) { gs += sc->raw_gsum[i]; ls += (double)sc->raw_loss[i]; }
-            double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
-            info[0] = done ? (double)loss : nan("");                   // multioptlrs.py:108-110
-            info[1] = (double)loss;
-            info[8] = gs / (RAW_DEPTH * (double)d.P);
-            info[9] = gs;
-            info[10] = ls / RAW_DEPTH;
-            info[11] = adjl;
-            info[14] = reward;                                         // baseenvironment.py:40
-            info[15] = (double)step;
-            a.reward[e] = (float)reward;
-            a.done[e] = done ? 1 : 0;
-            if (d.index_mode == B2E_INDEX_INTERNAL) {
-                const int cur = sc->cursor + 1;                        // optimize_nn.py:102-112
-                misc[4] = (cur * d.B >= d.N) ? 1.f : 0.f;
-                sc->cursor = (cur * d.B >= d.N) ? 0 : cur;
-            } else {
-                misc[4] = 0.f;
-            }
-        }
+        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
         __syncthreads();
         const bool wrap = misc[4] != 0.f;
         __syncthreads();
@@ -1919,7 +2012,7 @@ __global__ void info_finalize_kernel(Dev d, StepArgs a) {
         absadjg += in[0]; gdiff += in[1]; state += in[2];
     }
     double labs = 0.0;
-    for (int h = 0; h < d.H && h < sc->nvalid; ++h) {
+    for (int h = 0; d.col_l >= 0 && h < d.H && h < sc->nvalid; ++h) {
         int slot = sc->head - h;
         slot += slot < 0 ? d.H : 0;
         labs += (double)fabsf(sc->adj_loss[slot]);
@@ -1943,6 +2036,390 @@ __global__ void info_finalize_kernel(Dev d, StepArgs a) {
     info[7] = ssum;
     info[12] = absadjg / P;
     info[13] = gdiff / P;
+}
+
+// ---------------------------------------------------------------- MultiOptimize
+// envs/multioptimize.py:90-154 as a pipeline for every problem size:
+//   mo_update_kernel : w_t = w_{t-1} - delta(a); adjusted-weight ring; raw weight planes
+//   eval             : g_t, L_t and the step's scalars (eval_kernel<true> / MODE_EVAL_STEP)
+//   mo_obs_kernel    : adjusted-gradient ring, raw gradient planes, observation rows
+__global__ void __launch_bounds__(256) mo_update_kernel(const __grid_constant__ Dev d,
+                                                        const __grid_constant__ StepArgs a) {
+    const int e = a.e_begin + blockIdx.y;
+    const int seg = blockIdx.x;
+    const EnvScalars *sc = d.sc + e;
+    const int head_new = (sc->head + 1) % d.H;
+    float *wE = d.w + (size_t)e * d.Pp;
+    float *w2E = d.w2 ? d.w2 + (size_t)e * d.Pp : nullptr;
+    float *rw = d.col_w >= 0 ? d.ringw + ((size_t)e * d.H + head_new) * d.Pp : nullptr;
+    const float *act = a.actions + (size_t)e * d.P;
+    float s_absw = 0.f;
+    double s_lr = 0.0, s_lr2 = 0.0;
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        const int p = seg * UPD_SEG + (i * 256 + threadIdx.x) * 4;
+        if (p >= d.P) continue;
+        const float4 w4 = *reinterpret_cast<const float4 *>(wE + p);
+        float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w2E) o4 = *reinterpret_cast<const float4 *>(w2E + p);
+        const int4 r4 = d.row_lex ? *reinterpret_cast<const int4 *>(d.row_of_param + p)
+                                  : make_int4(p, p + 1, p + 2, p + 3);
+        const int rows[4] = {r4.x, r4.y, r4.z, r4.w};
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
+        float wn[4], aw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wn[j] = 0.f; aw[j] = 0.f;
+            if (p + j < d.P) {
+                const float delta = action_to_delta(act[rows[j]], d.act_ver);   // multioptimize.py:95-102
+                wn[j] = wv[j] - delta;                                          // :103
+                aw[j] = adjust_w(d.obs_ver, wn[j], wv[j], ov[j]);
+                s_absw += fabsf(wn[j]);
+                s_lr += (double)delta;
+                s_lr2 += (double)delta * (double)delta;
+            }
+        }
+        *reinterpret_cast<float4 *>(wE + p) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+        if (w2E) *reinterpret_cast<float4 *>(w2E + p) = w4;
+        if (rw) *reinterpret_cast<float4 *>(rw + p) = make_float4(aw[0], aw[1], aw[2], aw[3]);
+    }
+    __shared__ double red[8 * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double v0 = warp_sum((double)s_absw), v1 = warp_sum(s_lr), v2 = warp_sum(s_lr2);
+    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *out = d.part_u + ((size_t)e * d.nsegU + seg) * 4;
+        for (int i = 0; i < 3; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[w * 4 + i];
+            out[i] = v;
+        }
+    }
+}
+
+// Row-space observation kernel for every history layout / observation version
+// (utils/utils_env.py:9-47, 126-164; utils/utils_common.py:188-196): rows are
+// [key blocks in insertion order][depth values newest first], not clipped.
+__global__ void __launch_bounds__(OBS_WARPS * 32) mo_obs_kernel(const __grid_constant__ Dev d,
+                                                                const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ double red[OBS_WARPS * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = d.H, OD = d.OD;
+    float *obsL_s = sm;                                       // [B2E_MAX_HISTORY]
+    float *stage = sm + B2E_MAX_HISTORY + warp * (32 * OD + 8);
+    const int nitems = a.e_count * d.nseg;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int eo = item / d.nseg;
+        const int e = a.e_begin + eo;
+        const int seg = item - eo * d.nseg;
+        const EnvScalars *sc = d.sc + e;
+        const int head = sc->head, nvalid = sc->nvalid;      // already advanced by the eval stage
+        __syncthreads();
+        if (threadIdx.x < H) {
+            const int h = threadIdx.x;
+            float v = 0.f;
+            if (h < nvalid) {
+                int slot = head - h;
+                slot += slot < 0 ? H : 0;
+                v = sc->adj_loss[slot];
+            }
+            obsL_s[h] = v;
+        }
+        __syncthreads();
+        const float *gnew = d.gnext + (size_t)e * d.Pp;
+        float *gold = d.gprev + (size_t)e * d.Pp;
+        float *g2E = d.g2 ? d.g2 + (size_t)e * d.Pp : nullptr;
+        const float *rw = d.ringw + (size_t)e * H * d.Pp;
+        float *rg = d.ringg + (size_t)e * H * d.Pp;
+        float *rg_new = rg + (size_t)head * d.Pp;
+        float *obs_env = a.obs + (size_t)e * d.P * OD;
+        float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
+        for (int it = 0; it < OBS_ITERS; ++it) {
+            const int rbase = seg * SEG_ROWS + (it * OBS_WARPS + warp) * 32;
+            if (rbase >= d.P) break;
+            const int r = rbase + lane;
+            const bool ok = r < d.P;
+            const int p = ok ? (d.row_lex ? d.param_of_row[r] : r) : 0;
+            const float g = gnew[p], gp = gold[p];
+            const float g2 = g2E ? g2E[p] : 0.f;
+            const float ag = adjust_g(d.obs_ver, g, gp, g2);
+            if (ok) {
+                rg_new[p] = ag;
+                gold[p] = g;                                  // raw History shift
+                if (g2E) g2E[p] = gp;
+                s_absadjg += fabsf(ag);
+                s_gdiff += fabsf(g - gp);
+            }
+            const unsigned w_lo = (unsigned)rbase * OD;
+            const unsigned sh = (unsigned)((((size_t)e * d.P * OD) + w_lo) & 3);
+            float *srow = stage + sh + lane * OD;
+            for (int h = 0; h < H; ++h) {
+                float w1 = 0.f, g1 = 0.f;
+                if (h < nvalid) {
+                    int slot = head - h;
+                    slot += slot < 0 ? H : 0;
+                    if (d.col_w >= 0) w1 = rw[(size_t)slot * d.Pp + p];
+                    g1 = h > 0 ? rg[(size_t)slot * d.Pp + p] : ag;
+                }
+                if (ok) s_state += fabsf(w1) + fabsf(g1);
+                if (d.col_w >= 0) srow[d.col_w + h] = w1;
+                if (d.col_l >= 0) srow[d.col_l + h] = obsL_s[h];
+                srow[d.col_g + h] = g1;
+            }
+            __syncwarp();
+            const unsigned nw = (unsigned)min(32, d.P - rbase) * OD;
+            float *dst = obs_env + w_lo;
+            const float *src = stage + sh;
+            const unsigned head_w = min(nw, (4u - sh) & 3u);
+            const unsigned body_e = head_w + ((nw - head_w) & ~3u);
+            if (lane < head_w) dst[lane] = src[lane];
+            for (unsigned i = head_w + lane * 4; i < body_e; i += 128)
+                *reinterpret_cast<float4 *>(dst + i) = *reinterpret_cast<const float4 *>(src + i);
+            if (body_e + lane < nw) dst[body_e + lane] = src[body_e + lane];
+            __syncwarp();
+        }
+        const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+        const double v2 = warp_sum((double)s_state);
+        if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double *out = d.part + ((size_t)e * d.nseg + seg) * 4;
+            for (int i = 0; i < 3; ++i) {
+                double v = 0.0;
+                for (int w = 0; w < OBS_WARPS; ++w) v += red[w * 4 + i];
+                out[i] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- generic dense stack
+// Any `layers` tuple of the reference's create_neural_net (utils/utils_tf.py:74-86; default
+// (256, 256)) and any minibatch size (MultiOptimize's batch_size=None is the whole data set):
+// one CTA per env, activations and deltas in a per-CTA HBM/L2 workspace, every matmul a
+// 64x64x16 shared-memory tiled FFMA GEMM with 4x4 register tiles.  Slower than the
+// single-hidden-layer kernels above but shape-agnostic; it plugs into the same pipeline
+// (eval -> update -> eval -> observations).
+constexpr int GT_M = 64, GT_N = 64, GT_K = 16, GT_LD = 68;
+
+// C(m,n) = sum_k A(m,k) * B(k,n) with A(m,k) = A[m*am + k*ak], B(k,n) = Bm[k*bk + n*bn]
+template <class Epi>
+__device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak, const float *Bm,
+                           long bk, long bn, float *smA, float *smB, Epi epi) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    for (int m0 = 0; m0 < M; m0 += GT_M) {
+        for (int n0 = 0; n0 < N; n0 += GT_N) {
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int k0 = 0; k0 < K; k0 += GT_K) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = tid + j * 256;
+                    int mm, kk;
+                    if (ak == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+                    const int m = m0 + mm, k = k0 + kk;
+                    smA[kk * GT_LD + mm] = (m < M && k < K) ? A[m * am + k * ak] : 0.f;
+                    int nn, kb;
+                    if (bn == 1) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
+                    const int n = n0 + nn, k2 = k0 + kb;
+                    smB[kb * GT_LD + nn] = (n < N && k2 < K) ? Bm[k2 * bk + n * bn] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < GT_K; ++kk) {
+                    const float4 a4 = *reinterpret_cast<const float4 *>(smA + kk * GT_LD + ty * 4);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(smB + kk * GT_LD + tx * 4);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+                    if (m < M && n < N) epi(m, n, acc[i][j]);
+                }
+        }
+    }
+}
+
+__device__ double block_sum(double v, double *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) gen_eval_kernel(const __grid_constant__ Dev d,
+                                                       const __grid_constant__ StepArgs a) {
+    __shared__ __align__(16) float smA[GT_K * GT_LD];
+    __shared__ __align__(16) float smB[GT_K * GT_LD];
+    __shared__ double red[8];
+    __shared__ float misc[8];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int L = d.nlayers, B = d.B, C = d.C;
+    float *ws = d.ws + (size_t)blockIdx.x * d.ws_stride;
+    const int e_end = a.e_begin + a.e_count;
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        if (a.mode == MODE_RESET && a.mask != nullptr && !a.mask[e]) continue;
+        EnvScalars *sc = d.sc + e;
+        float *wE = d.w + (size_t)e * d.Pp;
+        const bool lrs = d.env_kind == B2E_ENV_MULTIOPTLRS;
+        __syncthreads();
+        if (a.mode == MODE_RESET) {                                   // base_reset
+            if (d.index_mode == B2E_INDEX_INTERNAL) {
+                shuffle_order(d, e, sc);                              // optimize_nn.py:114-120
+                if (tid == 0) sc->cursor = 0;
+                __syncthreads();
+            }
+            const int episode = sc->episode;
+            for (int l = 0; l < L; ++l) {                             // keras Dense defaults
+                const int nin = d.dims[l], nout = d.dims[l + 1];
+                const float limit = sqrtf(6.0f / (float)(nin + nout));
+                const int lo = d.woff[l], hi = d.boff[l] + nout;
+                for (int p = lo + tid; p < hi; p += nt) {
+                    float v = 0.f;
+                    if (a.init_params) v = a.init_params[(size_t)e * d.P + p];
+                    else if (p < d.boff[l]) v = glorot(d.seed, e, episode, p, limit);
+                    if (d.w2) d.w2[(size_t)e * d.Pp + p] = wE[p];
+                    wE[p] = v;
+                }
+            }
+            __syncthreads();
+        }
+        const int *idx; int cnt;
+        current_batch(d, a, e, sc, idx, cnt);
+        // ---- inputs
+        float *act0 = ws + d.aoff[0];
+        for (int i = tid; i < B * d.D; i += nt) {
+            const int s = i / d.D, k = i - s * d.D;
+            act0[i] = s < cnt ? d.X[(size_t)idx[s] * d.Dp + k] : 0.f;
+        }
+        __syncthreads();
+        // ---- forward (problems/optimize_nn.py:35-44)
+        for (int l = 0; l < L; ++l) {
+            const int nin = d.dims[l], nout = d.dims[l + 1];
+            const float *in = ws + d.aoff[l];
+            float *out = ws + d.aoff[l + 1];
+            const float *Wl = wE + d.woff[l], *bl = wE + d.boff[l];
+            const bool relu = l + 1 < L;
+            gemm_tiled(B, nout, nin, in, nin, 1, Wl, nout, 1, smA, smB,
+                       [&](int m, int n, float v) {
+                           v += bl[n];
+                           out[(size_t)m * nout + n] = relu ? fmaxf(v, 0.f) : v;
+                       });
+            __syncthreads();
+        }
+        // ---- softmax cross-entropy per sample (:47), delta of the logits
+        float *dl = ws + d.doff0;
+        const float *Z = ws + d.aoff[L];
+        double lsum = 0.0;
+        for (int s = tid; s < B; s += nt) {
+            float *dz = dl + (size_t)s * C;
+            if (s < cnt) {
+                const float *z = Z + (size_t)s * C;
+                const int y = d.labels[idx[s]];
+                float m = z[0];
+                for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) sum += expf(z[c] - m);
+                lsum += (double)((m + logf(sum)) - z[y]);
+                const float inv = 1.0f / sum;
+                for (int c = 0; c < C; ++c) dz[c] = expf(z[c] - m) * inv - (c == y ? 1.f : 0.f);
+            } else {
+                for (int c = 0; c < C; ++c) dz[c] = 0.f;
+            }
+        }
+        const float loss = (float)(block_sum(lsum, red) / (double)cnt);     // reduce_mean (:50)
+        // ---- backward: gradient of the batch SUM (:49)
+        float *gdst;
+        if (a.mode == MODE_RESET) gdst = d.gprev + (size_t)e * d.Pp;
+        else if (a.mode == MODE_EVAL) gdst = a.grad_out + (size_t)e * d.P;
+        else gdst = d.gnext + (size_t)e * d.Pp;
+        float *g2E = (a.mode == MODE_RESET && d.g2) ? d.g2 + (size_t)e * d.Pp : nullptr;
+        float gpart = 0.f;
+        for (int l = L - 1; l >= 0; --l) {
+            const int nin = d.dims[l], nout = d.dims[l + 1];
+            const float *in = ws + d.aoff[l];
+            float *gW = gdst + d.woff[l], *gb = gdst + d.boff[l];
+            const int wo = d.woff[l], bo = d.boff[l];
+            // kernel gradient: in^T . delta
+            gemm_tiled(nin, nout, B, in, 1, nin, dl, nout, 1, smA, smB,
+                       [&](int m, int n, float v) {
+                           const int p = m * nout + n;
+                           if (g2E) g2E[wo + p] = gW[p];
+                           gW[p] = v;
+                           gpart += v;
+                       });
+            for (int j = tid; j < nout; j += nt) {
+                float g = 0.f;
+                for (int s = 0; s < cnt; ++s) g += dl[(size_t)s * nout + j];
+                if (g2E) g2E[bo + j] = gb[j];
+                gb[j] = g;
+                gpart += g;
+            }
+            if (l > 0) {                                              // delta of the layer below
+                float *dn = ws + (dl == ws + d.doff0 ? d.doff1 : d.doff0);
+                const float *Wl = wE + d.woff[l];
+                gemm_tiled(B, nin, nout, dl, nout, 1, Wl, 1, nout, smA, smB,
+                           [&](int m, int n, float v) {
+                               dn[(size_t)m * nin + n] = in[(size_t)m * nin + n] > 0.f ? v : 0.f;
+                           });
+                dl = dn;
+            }
+            __syncthreads();
+        }
+        const double gsum = block_sum((double)gpart, red);
+        // ---- what the caller asked for
+        if (a.mode == MODE_EVAL) {
+            if (tid == 0) a.loss_out[e] = loss;
+        } else if (a.mode == MODE_EVAL_STEP) {
+            if (tid == 0) step_scalars(d, a, sc, e, loss, gsum, misc);
+            __syncthreads();
+            const bool wrap = misc[4] != 0.f;
+            __syncthreads();
+            if (wrap) shuffle_order(d, e, sc);
+        } else if (a.mode == MODE_RESET) {
+            if (tid == 0) {
+                if (lrs) {
+                    for (int i = 0; i < RAW_DEPTH; ++i) { sc->raw_loss[i] = 0.f; sc->raw_gsum[i] = 0.0; }
+                    sc->raw_pos = 0;
+                } else {
+                    sc->raw_pos = (sc->raw_pos + 1) % RAW_DEPTH;
+                }
+                for (int i = 0; i < B2E_MAX_HISTORY; ++i) sc->adj_loss[i] = 0.f;
+                sc->raw_loss[sc->raw_pos] = loss;
+                sc->raw_gsum[sc->raw_pos] = gsum;
+                sc->loss_prev = loss;
+                sc->head = d.H - 1;
+                sc->nvalid = 0;
+                sc->step = 0;
+                sc->episode = sc->episode + 1;
+            }
+            if (a.obs) {
+                float *o = a.obs + (size_t)e * d.P * d.OD;
+                const size_t n = (size_t)d.P * d.OD;
+                const float fill = lrs ? -1.0f : 0.0f;
+                for (size_t i = tid; i < n; i += nt) o[i] = fill;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------ utility kernels
@@ -2086,6 +2563,8 @@ struct b2e_env {
     EnvScalars *sc;
     size_t smem_obs;
     int chunk_envs, obs_grid;
+    bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
+    float *w2, *g2, *ws;
     int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
     size_t smem_obs2;
     Dev d_eval;                      // Dev with the eval kernel's shared-memory layout
@@ -2192,8 +2671,39 @@ int configure(b2e_handle h) {
         d.lim1 = sqrtf(6.0f / (float)(d.D + d.N1));
         d.lim2 = d.hidden ? sqrtf(6.0f / (float)(d.N1 + d.C)) : 0.f;
     }
+    // dense stack of the classifier; more than one hidden layer (or a shape the fused kernels
+    // cannot hold) runs the generic pipeline
+    int nhid = 0;
+    if (d.kind != B2E_PROBLEM_FUNC) {
+        d.dims[0] = d.D;
+        if (c.num_hidden > 0) {
+            d.dims[++nhid] = c.num_hidden;
+            for (int i = 0; i < B2E_MAX_LAYERS - 2 && c.hidden_more[i] > 0; ++i) d.dims[++nhid] = c.hidden_more[i];
+        }
+        d.dims[nhid + 1] = d.C;
+        d.nlayers = nhid + 1;
+        int p = 0;
+        for (int l = 0; l < d.nlayers; ++l) {
+            d.woff[l] = p; p += d.dims[l] * d.dims[l + 1];
+            d.boff[l] = p; p += d.dims[l + 1];
+        }
+        const char *force = getenv("B2E_FORCE_GENERIC");
+        d.generic = (nhid > 1 || (force && atoi(force) != 0 && d.kind == B2E_PROBLEM_SOFTMAX)) ? 1 : 0;
+        if (d.generic) d.P = p;
+    }
     d.Pp = round_up(d.P, 4);
+    d.col_w = 0; d.col_l = d.H; d.col_g = 2 * d.H;
     d.OD = 3 * d.H;
+    if (c.env_kind == B2E_ENV_MULTIOPTIMIZE) {                 // utils/utils_env.py:22-44
+        const int hv = c.history_version;
+        if (hv == 0 || hv == 2) d.H = 1;                       // History(1, ...)
+        const bool has_w = hv == 2 || hv == 3, has_l = hv == 1 || hv == 2 || hv == 3;
+        int col = 0;
+        d.col_w = has_w ? col : -1; col += has_w ? d.H : 0;
+        d.col_l = has_l ? col : -1; col += has_l ? d.H : 0;
+        d.col_g = col; col += d.H;
+        d.OD = col;
+    }
     d.Dp = round_up(d.D, 4);
     d.Ds = d.Dp;
     if (d.Ds > 0 && ((d.Ds >> 2) & 1) == 0) d.Ds += 4;       // odd number of float4 per row
@@ -2222,16 +2732,20 @@ int configure(b2e_handle h) {
     d.nsc = (d.B + 31) / 32;
     d.ncc = d.N1p / 8;
     while (d.nsc * d.ncc > nw * MAXI && h->nthreads < 256) { h->nthreads *= 2; nw *= 2; }
-    if (d.nsc * d.ncc > nw * MAXI)
-        return fail(h, "batch_size x layer width too large for the fused kernel "
-                       "(need ceil(B/32) * ceil(N1/8) <= 32)");
+    if (d.nsc * d.ncc > nw * MAXI) {
+        if (d.kind != B2E_PROBLEM_SOFTMAX)
+            return fail(h, "batch_size x layer width too large for the fused kernel "
+                           "(need ceil(B/32) * ceil(N1/8) <= 32)");
+        d.generic = 1;
+    }
     d.nks = 1;
     while (d.nsc * d.ncc * d.nks * 2 <= nw && d.KT / (d.nks * 2) >= 4 && !d.fast) d.nks *= 2;
     d.fitems = d.nsc * d.ncc * d.nks;
     if (d.fast) d.nks = 256 / (8 * d.cg);                      // K slices of the fast forward
     // large problems run as a pipeline of kernels (eval / update / eval / observations)
-    d.split = (d.fast && c.env_kind == B2E_ENV_MULTIOPTLRS &&
-               d.nks * d.B * d.N1p <= 2 * round_up(d.KT, 4) * d.N1p) ? 1 : 0;
+    h->use_eval_kernel = d.fast && d.nks * d.B * d.N1p <= 2 * round_up(d.KT, 4) * d.N1p;
+    if (d.generic) { h->use_eval_kernel = false; d.fast = 0; }
+    d.split = (c.env_kind == B2E_ENV_MULTIOPTIMIZE || h->use_eval_kernel || d.generic) ? 1 : 0;
     // shared memory carve-up (float offsets, all multiples of 4)
     d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
     int off = d.B * d.Ds + d.xslack;
@@ -2261,6 +2775,21 @@ int configure(b2e_handle h) {
     d.off_lb = off; off += round_up(d.B, 4);
     d.off_misc = off; off += 8 + 2 * B2E_MAX_HISTORY;
     h->smem_bytes = (size_t)off * sizeof(float);
+    if (!d.generic && h->smem_bytes > 227 * 1024 && d.kind == B2E_PROBLEM_SOFTMAX) {
+        d.generic = 1; d.fast = 0; d.split = 1;               // does not fit the fused kernel
+        h->use_eval_kernel = false;
+    }
+    if (d.generic) {
+        h->smem_bytes = 0;
+        int maxw = 0, o = 0;
+        for (int l = 0; l <= d.nlayers; ++l) {
+            d.aoff[l] = o; o += round_up(d.B * d.dims[l], 4);
+            if (l > 0 && d.dims[l] > maxw) maxw = d.dims[l];
+        }
+        d.doff0 = o; o += round_up(d.B * maxw, 4);
+        d.doff1 = o; o += round_up(d.B * maxw, 4);
+        d.ws_stride = o;
+    }
     {   // observation kernel variant: B2E_OBS = "<stages><b|s>" (cp.async gathers, e.g. "4b"),
         // "r<rows><b|s>" (register-batched gathers, e.g. "r4b"), "0" = obs_kernel;
         // b = cp.async.bulk row-block stores, s = 16-byte stores
@@ -2275,7 +2804,7 @@ int configure(b2e_handle h) {
             return fail(h, "B2E_OBS: stages must be 0, 3, 4 or 6");
         if (h->obs_regs != 0 && h->obs_regs != 1 && h->obs_regs != 2 && h->obs_regs != 4)
             return fail(h, "B2E_OBS: rows per lane must be 1, 2 or 4");
-        if (d.H != 5 || !d.split) h->obs_stages = h->obs_regs = 0;
+        if (d.H != 5 || !d.split || c.env_kind != B2E_ENV_MULTIOPTLRS) h->obs_stages = h->obs_regs = 0;
         if (h->obs_stages || h->obs_regs) {
             d.nseg = ((d.P + 31) / 32 + O2_UNITS - 1) / O2_UNITS;
             const int npl1 = 2 * d.H + 2, stg = 32 * d.OD + 8;
@@ -2315,6 +2844,13 @@ int configure(b2e_handle h) {
 int launch(b2e_handle h, StepArgs args, void *stream) {
     if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
     const cudaStream_t cs = (cudaStream_t)stream;
+    if (h->d.generic) {
+        // MODE_RESET / MODE_EVAL / MODE_EVAL_STEP / MODE_EVAL_FIRST of the generic dense stack
+        gen_eval_kernel<<<h->grid, 256, 0, cs>>>(h->d, args);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
     if (h->d.fast) {
         if (h->d.H == 5) optenv_kernel<5, true><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
         else optenv_kernel<0, true><<<h->grid, h->nthreads, h->smem_bytes, cs>>>(h->d, args);
@@ -2341,15 +2877,23 @@ int b2e_num_params(b2e_handle h) { return h ? h->d.P : -1; }
 
 int b2e_obs_dim(b2e_handle h) { return h ? h->d.OD : -1; }
 
+int b2e_history_depth(b2e_handle h) { return h ? h->d.H : -1; }
+
 int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (!cfg || !out) return fail(nullptr, "b2e_create: null argument");
     if (cfg->struct_size != (int32_t)sizeof(b2e_config))
         return fail(nullptr, "b2e_create: b2e_config.struct_size mismatch (ABI skew)");
-    if (cfg->env_kind != B2E_ENV_MULTIOPTLRS)
-        return fail(nullptr, "b2e_create: env_kind not supported (MultiOptLRs only in this build)");
-    if (cfg->history_version != 3 || cfg->observation_version != 3)
+    if (cfg->env_kind != B2E_ENV_MULTIOPTLRS && cfg->env_kind != B2E_ENV_MULTIOPTIMIZE)
+        return fail(nullptr, "b2e_create: unknown env_kind");
+    if (cfg->env_kind == B2E_ENV_MULTIOPTLRS && (cfg->history_version != 3 || cfg->observation_version != 3))
         return fail(nullptr, "b2e_create: MultiOptLRs is history_version 3 / observation_version 3 "
                              "(reference envs/multioptlrs.py:61)");
+    // history version 5 exists in utils_env.py:38-42 but MultiOptimize cannot feed it
+    // (History.append asserts on the missing 'weights' key, utils_common.py:183)
+    if (cfg->env_kind == B2E_ENV_MULTIOPTIMIZE &&
+        (cfg->history_version < 0 || cfg->history_version > 4 || cfg->observation_version < 0 ||
+         cfg->observation_version > 3 || cfg->action_version > 1))
+        return fail(nullptr, "b2e_create: bad history/observation/action version (RuntimeError in the reference)");
     if (cfg->action_version < 0 || cfg->action_version > 3 || cfg->reward_version < 0 ||
         cfg->reward_version > 6)
         return fail(nullptr, "b2e_create: bad action/reward version (RuntimeError in the reference)");
@@ -2373,6 +2917,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->trace = false; h->tr_count = 0;
     for (auto &ev : h->tr) ev = nullptr;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
+    h->w2 = h->g2 = h->ws = nullptr;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
@@ -2385,42 +2930,56 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return bail("b2e_create: problem does not fit the fused kernel's shared memory (" +
                     std::to_string(h->smem_bytes) + " bytes needed)");
+    const bool h5 = h->d.H == 5;
     const void *kernel_fn = h->d.fast
-        ? (cfg->max_history == 5 ? (const void *)optenv_kernel<5, true> : (const void *)optenv_kernel<0, true>)
-        : (cfg->max_history == 5 ? (const void *)optenv_kernel<5, false> : (const void *)optenv_kernel<0, false>);
-    if (cudaFuncSetAttribute(kernel_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)h->smem_bytes) != cudaSuccess)
-        return bail("b2e_create: cudaFuncSetAttribute(smem) failed");
-    int occ = 0;
-    cudaError_t occ_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_fn, h->nthreads,
-                                                                        h->smem_bytes);
-    if (occ_err != cudaSuccess || occ < 1)
-        return bail("b2e_create: kernel does not fit an SM");
-    const long long resident = (long long)occ * h->num_sms;
-    h->grid = (int)(cfg->num_envs < resident ? cfg->num_envs : resident);
+        ? (h5 ? (const void *)optenv_kernel<5, true> : (const void *)optenv_kernel<0, true>)
+        : (h5 ? (const void *)optenv_kernel<5, false> : (const void *)optenv_kernel<0, false>);
     Dev &d = h->d;
+    if (d.generic) {
+        // per-CTA workspace of the generic dense stack; at most 4 GB of it
+        const size_t ws_bytes = (size_t)d.ws_stride * sizeof(float);
+        long long ctas = (long long)(((size_t)4 << 30) / ws_bytes);
+        if (ctas < 1) ctas = 1;
+        if (ctas > 2LL * h->num_sms) ctas = 2LL * h->num_sms;
+        if (ctas > cfg->num_envs) ctas = cfg->num_envs;
+        h->grid = (int)ctas;
+        if (cudaMalloc((void **)&h->ws, ws_bytes * (size_t)ctas) != cudaSuccess)
+            return bail("b2e_create: cudaMalloc of the dense-stack workspace failed (" +
+                        std::to_string(ws_bytes * (size_t)ctas) + " bytes)");
+    } else {
+        if (cudaFuncSetAttribute(kernel_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_bytes) != cudaSuccess)
+            return bail("b2e_create: cudaFuncSetAttribute(smem) failed");
+        int occ = 0;
+        cudaError_t occ_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_fn, h->nthreads,
+                                                                            h->smem_bytes);
+        if (occ_err != cudaSuccess || occ < 1)
+            return bail("b2e_create: kernel does not fit an SM");
+        const long long resident = (long long)occ * h->num_sms;
+        h->grid = (int)(cfg->num_envs < resident ? cfg->num_envs : resident);
+    }
     const size_t EP = (size_t)d.E * d.Pp;
     auto dmalloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
     if (!dmalloc((void **)&h->w, EP * 4) || !dmalloc((void **)&h->gprev, EP * 4) ||
         !dmalloc((void **)&h->ringw, EP * d.H * 4) || !dmalloc((void **)&h->ringg, EP * d.H * 4) ||
         !dmalloc((void **)&h->sc, (size_t)d.E * sizeof(EnvScalars)))
         return bail("b2e_create: cudaMalloc of env state failed");
+    if (cfg->env_kind == B2E_ENV_MULTIOPTIMIZE && cfg->observation_version == 2) {
+        if (!dmalloc((void **)&h->w2, EP * 4) || !dmalloc((void **)&h->g2, EP * 4))
+            return bail("b2e_create: cudaMalloc of the raw-history planes failed");
+        cudaMemset(h->w2, 0, EP * 4); cudaMemset(h->g2, 0, EP * 4);
+    }
     if (d.split) {
         if (!dmalloc((void **)&h->gnext, EP * 4) ||
             !dmalloc((void **)&h->part, (size_t)d.E * d.nseg * 4 * sizeof(double)) ||
             !dmalloc((void **)&h->part_u, (size_t)d.E * d.nsegU * 4 * sizeof(double)))
             return bail("b2e_create: cudaMalloc of the split-path buffers failed");
         cudaMemset(h->gnext, 0, EP * 4);
-        int prio_least = 0, prio_greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-        if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
-            return bail("b2e_create: stream/event creation failed");
-        for (auto &ev : h->ev_chunk)
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
-                return bail("b2e_create: event creation failed");
+        if (cudaFuncSetAttribute(mo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_obs) != cudaSuccess)
+            return bail("b2e_create: observation kernel does not fit (max_history too large)");
+    }
+    if (d.split) {
         if (cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_obs) != cudaSuccess ||
             cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2429,11 +2988,9 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if ((h->obs_stages || h->obs_regs) &&
             cudaFuncSetAttribute(obs2_fn(h->obs_stages, h->obs_regs, h->obs_bulk), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_obs2) != cudaSuccess)
-            return bail("b2e_create: observation kernel (async gathers) does not fit shared memory");
-        // kernels that share an SM must agree on its L1/shared-memory split
-        cudaFuncSetAttribute(obs_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(obs_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(kernel_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return bail("b2e_create: observation kernel (batched gathers) does not fit shared memory");
+    }
+    if (h->use_eval_kernel) {
         if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess ||
             cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2482,7 +3039,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     }
     d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
     d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part; d.part_u = h->part_u;
-    d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc;
+    d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc; d.w2 = h->w2; d.g2 = h->g2; d.ws = h->ws;
     d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param; d.param_of_row = h->param_of_row;
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
@@ -2494,6 +3051,7 @@ void b2e_destroy(b2e_handle h) {
     if (!h) return;
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
+    cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws);
     cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
@@ -2574,9 +3132,41 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     a.mode = MODE_STEP; a.actions = actions; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
     a.obs = obs_out; a.reward = reward_out; a.done = done_out; a.info = info_out;
     if (!h->d.split) return launch(h, a, stream);
-    // ---- large problems: eval(w) -> update -> eval(w') -> observations, all on the caller's stream
     cudaStream_t main_s = (cudaStream_t)stream;
     Dev &d = h->d;
+    if (d.env_kind == B2E_ENV_MULTIOPTIMIZE) {
+        // ---- update -> eval(w') + scalars -> observations (envs/multioptimize.py:90-154)
+        a.e_begin = 0; a.e_count = d.E;
+        mo_update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        if (h->use_eval_kernel) {
+            Dev &v = h->d_eval;
+            v.gprev = d.gprev; v.gnext = d.gnext; v.perm_stride = d.perm_stride;
+            v.X = d.X; v.labels = d.labels; v.targets = d.targets; v.w = d.w; v.sc = d.sc;
+            v.ord = d.ord; v.perm = d.perm;
+            const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
+            eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
+        } else {
+            StepArgs b = a;
+            b.mode = MODE_EVAL_STEP;
+            if (launch(h, b, main_s)) return 1;
+        }
+        mo_obs_kernel<<<d.nseg * d.E, OBS_WARPS * 32, h->smem_obs, main_s>>>(d, a);
+        info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
+        h->launches += 2;
+        CUDA_TRY(h, cudaGetLastError());
+        if (d.auto_reset) {
+            StepArgs r;
+            memset(&r, 0, sizeof(r));
+            r.mode = MODE_RESET; r.mask = done_out; r.obs = obs_out;
+            return launch(h, r, main_s);
+        }
+        return 0;
+    }
+    // ---- large problems: eval(w) -> update -> eval(w') -> observations, all on the caller's stream
     {
         Dev &v = h->d_eval;                                  // same pointers, eval-kernel smem layout
         v.gprev = d.gprev; v.gnext = d.gnext; v.perm_stride = d.perm_stride;
@@ -2588,11 +3178,25 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
     auto mark = [&](int i) { if (h->trace) cudaEventRecord(h->tr[i], main_s); };
     mark(0);
-    eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    if (h->use_eval_kernel) {
+        eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    } else {                                                 // generic dense stack
+        StepArgs b = a;
+        b.mode = MODE_EVAL_FIRST;
+        if (launch(h, b, main_s)) return 1;
+        h->launches--;
+    }
     mark(1);
     update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
-    eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    if (h->use_eval_kernel) {
+        eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    } else {
+        StepArgs b = a;
+        b.mode = MODE_EVAL_STEP;
+        if (launch(h, b, main_s)) return 1;
+        h->launches--;
+    }
     mark(3);
     {
         const int items = d.nseg * d.E;

@@ -103,7 +103,9 @@ class DeviceEnvFront(BaseMultiEnvironment):
         obs, reward, done, info = backend.step(torch.as_tensor(flat, device=backend.device))
         info_row = info[0].cpu().numpy()
         self.current_step = int(info_row[15])
-        return (self._agent_dict(obs.cpu().numpy()), float(reward[0].item()), bool(done[0].item()),
+        # the reward of the step is the double in info (info['episode']['r'] is the very same
+        # object in the reference, baseenvironment.py:40); reward_out is its float32 copy
+        return (self._agent_dict(obs.cpu().numpy()), float(info_row[14]), bool(done[0].item()),
                 info_row_to_dict(info_row))
 
     def render(self, mode='human'):

@@ -88,7 +88,9 @@ class _DeviceProblem(BaseProblem):
 class OptimizeNN(_DeviceProblem):
     """Dense stack + softmax cross-entropy on a data set (reference
     problems/optimize_nn.py:22-64).  ``layers`` are the hidden widths (relu); the reference
-    builds them with ``model_fn`` / ``create_neural_net(layers=(256, 256))``."""
+    builds them with ``model_fn`` / ``create_neural_net(layers=(256, 256))``.  Zero or one
+    hidden layer runs the fused / streamed-operand kernels, deeper stacks the generic
+    tiled-GEMM pipeline of libb200env.so."""
 
     def __init__(self, model_fn=None, data_set=None, layers=None):
         super().__init__()
@@ -105,11 +107,6 @@ class OptimizeNN(_DeviceProblem):
                     'fused kernel; pass layers=(hidden_units,) or a model_fn with a .layers tuple')
             layers = (256, 256)                 # utils/utils_tf.py:74
         layers = tuple(int(h) for h in layers)
-        if len(layers) > 1:
-            raise NotImplementedError(
-                'OptimizeNN: the fused sm_100a kernel supports zero or one hidden layer; '
-                'layers=%r (the reference default is (256, 256)) is not built yet -- '
-                'pass layers=() or layers=(h,)' % (layers,))
         features = np.asarray(data_set.features)
         targets = np.asarray(data_set.targets)
         num_outputs = targets.shape[1] if targets.ndim == 2 else int(targets.max()) + 1

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define B2E_ABI_VERSION 1
+#define B2E_ABI_VERSION 2
 
 /* env_kind */
 #define B2E_ENV_MULTIOPTLRS   0   /* envs/multioptlrs.py:39-129   */
@@ -38,11 +38,12 @@ extern "C" {
 
 #define B2E_INFO_STRIDE 16        /* doubles per env in info_out, see b2e_step                       */
 #define B2E_MAX_HISTORY 32
+#define B2E_MAX_LAYERS 8          /* Dense layers of the classifier, output layer included           */
 
 /* b2e_get_state / b2e_set_state selectors (per-env stride in elements in brackets) */
 #define B2E_STATE_PARAMS      0   /* float  [P]   current parameters, natural (flatten_arrays) order */
 #define B2E_STATE_GRAD_PREV   1   /* float  [P]   newest raw-history gradient                         */
-#define B2E_STATE_ADJ_WEIGHTS 2   /* float  [H,P] adjusted weights history, NEWEST FIRST              */
+#define B2E_STATE_ADJ_WEIGHTS 2   /* float  [H,P] adjusted weights history, NEWEST FIRST (H = b2e_history_depth) */
 #define B2E_STATE_ADJ_GRADS   3   /* float  [H,P] adjusted gradients history, NEWEST FIRST            */
 #define B2E_STATE_ADJ_LOSSES  4   /* float  [H]   adjusted loss history, NEWEST FIRST                 */
 #define B2E_STATE_RAW_LOSSES  5   /* float  [5]   raw loss history, NEWEST FIRST                      */
@@ -59,7 +60,8 @@ typedef struct b2e_config {
     int32_t  env_kind;
     int32_t  problem_kind;
     int32_t  num_features;        /* D */
-    int32_t  num_hidden;          /* units of the single relu hidden layer, 0 = none */
+    int32_t  num_hidden;          /* units of the first relu hidden layer, 0 = none
+                                     (utils/utils_tf.py:74-86 create_neural_net) */
     int32_t  num_outputs;         /* C */
     int32_t  num_rows;            /* N rows in the data set */
     int32_t  batch_size;          /* B (load_data default 32, data/load_data.py:47) */
@@ -76,6 +78,8 @@ typedef struct b2e_config {
                                      of such an env holds the RESET observation
                                      (vectorize/concurrentvecenv.py:32-38) */
     int32_t  reserved;
+    int32_t  hidden_more[B2E_MAX_LAYERS]; /* widths of the 2nd, 3rd ... hidden layers, 0 terminated
+                                     (the reference default is layers=(256, 256)) */
     uint64_t init_seed;           /* seed of the on-device Glorot-uniform initialiser */
 } b2e_config;
 
@@ -89,6 +93,8 @@ int b2e_abi_version(void);
 
 int b2e_num_params(b2e_handle h);   /* BaseProblem.size, problems/base_problem.py:65-68 */
 int b2e_obs_dim(b2e_handle h);      /* observation_space.shape[0], utils/utils_env.py:22-44 */
+int b2e_history_depth(b2e_handle h); /* depth of the adjusted History: max_history, or 1 for
+                                       MultiOptimize history versions 0 and 2 (utils_env.py:22-31) */
 
 /* load_data / InMemoryDataSet.__init__ (data/load_data.py:47-112, dataset/inmemorydataset.py:11-15).
  * features [N,D] float32 row-major; targets: int32 labels [N] (softmax) or float32 [N,C]

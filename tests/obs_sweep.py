@@ -15,10 +15,12 @@ parser.add_argument('--envs', type=int, default=2048)
 parser.add_argument('--steps', type=int, default=12)
 parser.add_argument('--variants', default='0,r1s,r1b,r2s,r2b,r4s,r4b,3s,3b,4s,4b,6s,6b')
 parser.add_argument('--row-order', default='lexicographic')
+parser.add_argument('--hidden', default='64', help='comma separated hidden widths, empty for none')
 args = parser.parse_args()
 
 rng = np.random.RandomState(0)
-spec, rows = ProblemSpec('softmax', 784, (64,), 10), 60000
+hidden = tuple(int(h) for h in args.hidden.split(',') if h)
+spec, rows = ProblemSpec('softmax', 784, hidden, 10), 60000
 feats = rng.uniform(size=(rows, spec.num_features)).astype(np.float32)
 labels = rng.randint(0, spec.num_outputs, rows).astype(np.int32)
 perm = np.arange(rows, dtype=np.int32)

@@ -29,7 +29,12 @@ def run(name, spec, num_rows, num_envs, order, steps=20):
     env.close()
 
 if __name__ == '__main__':
-    for order in ('natural', 'lexicographic'):
+    import os
+    os.environ['B2E_FORCE_GENERIC'] = '1'
+    run('cfg3 softmax 784->10 GENERIC', ProblemSpec('softmax', 784, (), 10), 60000, 1024, 'lexicographic')
+    run('mlp 784->256->256->10', ProblemSpec('softmax', 784, (256, 256), 10), 60000, 512, 'lexicographic', steps=5)
+    del os.environ['B2E_FORCE_GENERIC']
+    for order in ('lexicographic',):
         run('cfg2 softmax 4->3', ProblemSpec('softmax', 4, (), 3), 150, 1024, order)
         run('cfg3 softmax 784->10', ProblemSpec('softmax', 784, (), 10), 60000, 1024, order)
         run('cfg4 mlp 784->64->10', ProblemSpec('softmax', 784, (64,), 10), 60000, 592, order, steps=10)

@@ -17,10 +17,14 @@ pytestmark = pytest.mark.gpu
 def test_env_step_and_reset_types():
     from custom_envs.envs import SINGLE_AGENT_ENVIRONMENTS
     for env_cls in SINGLE_AGENT_ENVIRONMENTS:
-        env = env_cls()                                   # default problem: Rosenbrock
+        env = env_cls()       # defaults: Rosenbrock (MultiOptLRs), iris + (256, 256) stack (MultiOptimize)
         state = env.reset()
         assert env.current_step == 0 and env.observation_space.contains(state)
         action = env.action_space.sample()
+        if env_cls.__name__ == 'MultiOptimize':
+            # +-4 is a step of +-10 on every weight (multioptimize.py:95-98): keep the run inside
+            # the declared +-1e6 observation box
+            action = type(action)((key, value * 0.25) for key, value in action.items())
         for i in range(1, 10):
             state, reward, terminal, info = env.step(action)
             assert env.current_step == i
@@ -65,11 +69,14 @@ def test_multioptlrs_nn_on_iris_matches_oracle():
     env.close()
 
 
-@pytest.mark.parametrize('name', ['func', 'nn'])
+@pytest.mark.parametrize('name', ['func', 'nn', 'nn-default'])
 def test_base_problem_contract(name):
     from custom_envs.problems import get_problem
-    kwargs = {} if name == 'func' else dict(layers=(8,))
+    kwargs = dict(layers=(8,)) if name == 'nn' else {}    # nn-default: the reference's (256, 256)
+    default = name == 'nn-default'
+    name = name.split('-')[0]
     problem = get_problem(name, **kwargs)
+    assert not default or problem.size == 4 * 256 + 256 + 256 * 256 + 256 + 256 * 3 + 3
     old = np.random.rand(problem.size)
     problem.set_parameters(old)
     assert np.allclose(problem.get_parameters(), old, atol=1e-6)        # set -> get round trip
@@ -83,8 +90,6 @@ def test_base_problem_contract(name):
         before = problem.get_loss()
         problem.next()
         assert problem.get_loss() != before                             # next minibatch
-        with pytest.raises(NotImplementedError):
-            get_problem('nn')                                           # (256, 256): not built
     with pytest.raises(RuntimeError):
         get_problem('other')
 

@@ -27,7 +27,7 @@ from oracle import optenv_oracle as orc
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'optlrs_*.npz')))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'opt*.npz')))
 
 
 def _mods():
@@ -71,6 +71,25 @@ def shift_ill(ill, depth, new_w, new_g):
     return out
 
 
+def unclipped_obs_err(obs, want, obs_version):
+    """Error of MultiOptimize observation rows (not clipped, envs/multioptimize.py:126-129).
+
+    * nan_to_num(x/0) is +-1.8e308 in the reference's float64 rows and +-FLT_MAX in float32
+      rows (the declared dtype of the observation space): such entries must agree in sign.
+    * observation version 2 (utils/utils_env.py:145-152) divides DIFFERENCES of consecutive
+      float32 losses / gradients / weights by (|difference| + 1e-3 or 1e-8): rounding noise of
+      1e-7 relative in the inputs is amplified by up to 1e3..1e4, so its bar is 2e-3.
+    Returns (err, threshold)."""
+    err = np.abs(obs - want) / np.maximum(1.0, np.abs(want))
+    big = np.abs(want) > 3e38
+    err[big] = np.where((np.sign(obs[big]) == np.sign(want[big])) & (np.abs(obs[big]) > 3e38), 0.0, 1.0)
+    return err, (2e-3 if obs_version == 2 else 1e-4)
+
+
+def reward_tol(obs_version):
+    return dict(rtol=5e-3, atol=5e-3) if obs_version == 2 else dict(rtol=1e-4, atol=1e-4)
+
+
 SPECS = {
     'iris_softmax': (orc.ProblemSpec('softmax', 4, (), 3), 150, 32, 6),
     'mlp_small': (orc.ProblemSpec('softmax', 6, (5,), 3), 50, 16, 3),
@@ -79,6 +98,11 @@ SPECS = {
     'mlp_784x64x10': (orc.ProblemSpec('softmax', 784, (64,), 10), 600, 32, 3),
     'odd_shapes': (orc.ProblemSpec('softmax', 49, (10,), 7), 101, 20, 2),
     'func': (orc.ProblemSpec('func', 0, (), 0), 0, None, 4),
+    # generic dense-stack pipeline: more than one hidden layer (the reference default is
+    # layers=(256, 256), utils/utils_tf.py:74) and the whole data set as one batch
+    'mlp_two_hidden': (orc.ProblemSpec('softmax', 12, (16, 8), 4), 60, 20, 3),
+    'mlp_256x256_iris': (orc.ProblemSpec('softmax', 4, (256, 256), 3), 150, 32, 2),
+    'full_batch': (orc.ProblemSpec('softmax', 4, (8,), 3), 150, 150, 2),
 }
 
 
@@ -114,12 +138,19 @@ def test_loss_and_gradient_match_oracle(name):
     env.close()
 
 
-@pytest.mark.parametrize('row_order', ['lexicographic', 'natural'])
+@pytest.mark.parametrize('row_order', ['lexicographic', 'natural', 'lexicographic-generic'])
 @pytest.mark.parametrize('name', list(SPECS))
-def test_step_parity_from_identical_states(name, row_order):
-    """Per-step parity with host-supplied minibatch indices (external index mode)."""
+def test_step_parity_from_identical_states(name, row_order, monkeypatch):
+    """Per-step parity with host-supplied minibatch indices (external index mode).
+    ``-generic`` forces the shape-agnostic dense-stack pipeline onto shapes the fused kernels
+    also cover, so both implementations are held to the same oracle."""
     BatchedOptEnv, _ = _mods()
     spec, num_rows, batch, num_envs = SPECS[name]
+    if row_order.endswith('-generic'):
+        if spec.kind != 'softmax' or name in ('mlp_784x64x10', 'softmax_784x10') or len(spec.hidden) > 1:
+            pytest.skip('generic path: softmax stacks; large / already-generic specs run it elsewhere')
+        monkeypatch.setenv('B2E_FORCE_GENERIC', '1')
+        row_order = 'lexicographic'
     func = spec.kind == 'func'
     feats, targs = (None, None) if func else make_data(spec, num_rows)
     rng = np.random.RandomState(2)
@@ -223,6 +254,10 @@ def test_golden_reference_runs_on_device(path):
     BatchedOptEnv, _ = _mods()
     fix = dict(np.load(path, allow_pickle=False))
     kwargs = dict(zip([str(k) for k in fix['env_kwargs_keys']], [int(v) for v in fix['env_kwargs_vals']]))
+    optimize = str(fix['env_kind']) == 'optimize'
+    if optimize:                 # MultiOptimize(version=...) is the history layout
+        kwargs['history_version'] = kwargs.pop('version')
+        kwargs['env_kind'] = 'optimize'
     spec = orc.ProblemSpec(str(fix['problem_kind']), int(fix['num_features']),
                            tuple(int(h) for h in fix['hidden']), int(fix['num_outputs']))
     num_envs = int(fix['num_envs'])
@@ -263,15 +298,85 @@ def test_golden_reference_runs_on_device(path):
         if done_np.any():
             obs_np = env.reset(env_mask=done_np, init_params=params()).cpu().numpy()
         reset_no += done_np
-        batch_no += 1 + done_np
+        # MultiOptLRs moves to the next minibatch every step (multioptlrs.py:128);
+        # MultiOptimize only when the problem is reset
+        batch_no += done_np if optimize else 1 + done_np
         check_batches()
         assert np.array_equal(np.repeat(done_np, num_params), fix['dones'][t]), t
         want = fix['states'][t]
-        err = np.abs(obs_np - want) / np.maximum(1.0, np.abs(want + 1))
-        assert np.mean(err <= 1e-4) > 0.97, (t, float(np.mean(err <= 1e-4)))
-        np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], rtol=1e-4, atol=1e-4)
+        if optimize:
+            obs_ver = kwargs['observation_version']
+            err, bar = unclipped_obs_err(obs_np, want, obs_ver)
+            assert np.mean(err <= bar) > 0.97, (t, float(np.mean(err <= bar)))
+            np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], **reward_tol(obs_ver))
+            got = env.info_dict(info)
+            for key in ('batch_loss', 'weights_mean', 'weights_sum', 'actions_mean', 'actions_std',
+                        'loss_mean', 'adjusted_loss', 'grad_diff'):
+                tol = reward_tol(obs_ver) if key == 'adjusted_loss' else dict(rtol=2e-4, atol=1e-5)
+                np.testing.assert_allclose(got[key], fix['info_' + key][t],
+                                           err_msg='%s step %d' % (key, t), **tol)
+        else:
+            err = np.abs(obs_np - want) / np.maximum(1.0, np.abs(want + 1))
+            assert np.mean(err <= 1e-4) > 0.97, (t, float(np.mean(err <= 1e-4)))
+            np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], rtol=1e-4, atol=1e-4)
         clipped_ok += 1
     assert clipped_ok == fix['actions'].shape[0]
+    env.close()
+
+
+@pytest.mark.parametrize('obs_version', [0, 1, 2, 3])
+@pytest.mark.parametrize('hist_version', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('name', ['mlp_small', 'mlp_784x64x10'])
+def test_multioptimize_trajectory_matches_oracle(name, hist_version, obs_version):
+    """envs/multioptimize.py:78-154 on the device against the oracle: same initial parameters,
+    same minibatch stream, same actions, several steps across an episode boundary.  The
+    large spec runs the streamed-operand eval kernel, the small one the generic path."""
+    if name == 'mlp_784x64x10' and (hist_version, obs_version) not in ((3, 2), (1, 0), (4, 3), (2, 1)):
+        pytest.skip('large spec: one layout per observation version')
+    BatchedOptEnv, _ = _mods()
+    spec, num_rows, batch, num_envs = SPECS[name]
+    feats, targs = make_data(spec, num_rows)
+    rng = np.random.RandomState(7)
+    max_batches, depth = 4, 3
+    perms = np.stack([orc.env_permutation(num_rows, 20 + s) for s in range(num_envs)])
+    cfg = orc.EnvConfig.multioptimize(hist_version, max_batches, depth, obs_version,
+                                      action_version=1, reward_version=(hist_version + obs_version) % 7)
+    env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch,
+                        max_batches=max_batches, max_history=depth, env_kind='optimize',
+                        history_version=hist_version, observation_version=obs_version,
+                        action_version=1, reward_version=cfg.reward_version, perms=perms,
+                        auto_reset=False)
+    ref = orc.OptVecEnvOracle(orc.BatchedOptEnvOracle(spec, feats, targs, num_envs, batch_size=batch,
+                                                      config=cfg, perms=perms))
+    num_params = ref.env.num_params
+    assert env.obs_dim == ref.env.obs_dim
+    init = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
+    obs = env.reset(init_params=init).cpu().numpy()
+    want = ref.reset(init_params=init)
+    assert np.array_equal(obs, want.astype(np.float32)) and not obs.any()
+    for t in range(2 * max_batches + 2):
+        actions = rng.uniform(-20, 20, size=env.num_rows).astype(np.float32)   # deltas up to 2e-2
+        init = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
+        obs, rew, done, info = env.step(torch.as_tensor(actions, device=env.device))
+        done_np = done.cpu().numpy().astype(bool)
+        rew_np = rew.cpu().numpy().copy()
+        got = env.info_dict(info)
+        obs_np = obs.cpu().numpy().copy()
+        if done_np.any():
+            obs_np = env.reset(env_mask=done_np, init_params=init).cpu().numpy().copy()
+        want_obs, want_rew, want_done, want_info = ref.step(actions, reset_params=init)
+        tag = (name, hist_version, obs_version, t)
+        assert np.array_equal(np.repeat(done_np, num_params), want_done), tag
+        assert done_np.all() == ((t + 1) % max_batches == 0), tag
+        err, bar = unclipped_obs_err(obs_np, want_obs, obs_version)
+        assert np.mean(err <= bar) > 0.97, (tag, float(np.mean(err <= bar)))
+        assert np.median(err) <= (20 if obs_version == 2 else 1) * RTOL, (tag, float(np.median(err)))
+        np.testing.assert_allclose(np.repeat(rew_np, num_params), want_rew, err_msg=str(tag),
+                                   **reward_tol(obs_version))
+        for key in ('batch_loss', 'weights_mean', 'weights_sum', 'actions_mean', 'actions_std',
+                    'loss_mean', 'adjusted_loss', 'grad_diff'):
+            tol = reward_tol(obs_version) if key == 'adjusted_loss' else dict(rtol=2e-4, atol=1e-6)
+            np.testing.assert_allclose(got[key], want_info[key], err_msg=str(tag + (key,)), **tol)
     env.close()
 
 

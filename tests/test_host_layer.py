@@ -69,8 +69,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.b2e_abi_version() == 1
-    assert ctypes.sizeof(_lib.Config) == 88
+    assert lib.b2e_abi_version() == 2
+    assert ctypes.sizeof(_lib.Config) == 120
 
 
 def test_create_fails_loudly_without_gpu_or_on_bad_config():
