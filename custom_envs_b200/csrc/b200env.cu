@@ -1928,6 +1928,169 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
     }
 }
 
+// ------------------------------------------------ thin eval kernel: no hidden layer
+// Softmax regression (BASELINE config 3: 784 -> 10): logits Z = X.W + b with at most 16
+// classes.  There is almost no arithmetic (1 MFLOP per env), the kernel is the minibatch
+// gather: X rows travel with 16-byte cp.async into shared memory once and serve the forward
+// and the backward pass; W sits beside it padded to 4-float groups.
+//   forward : warp = 4 samples at a time, lanes stride over k, W row read as float4s
+//   backward: thread = one feature k, all classes, all samples; gradient staged in shared
+//             memory and written with coalesced 16-byte stores
+constexpr int THIN_CMAX = 16;
+
+template <bool SECOND>
+__global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ Dev d,
+                                                           const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float misc[8];
+    __shared__ double red[NSTAT * 8];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = d.D, C = d.C, B = d.B, XS = d.Ds;
+    const int Cq = (C + 3) & ~3;
+    float *Xs = sm;                                   // [B][XS]
+    float *Ws = Xs + B * XS;                          // [D][Cq], later the gradient [D][C]
+    float *bs = Ws + D * Cq;                          // [Cq]
+    float *Zs = bs + THIN_CMAX;                       // [B][Cq] logits, then dZ
+    float *lb = Zs + B * THIN_CMAX;                   // [B]
+    int *idx_s = reinterpret_cast<int *>(lb + B);     // [B]
+    int *ys = idx_s + B;                              // [B]
+    const int e_end = a.e_begin + a.e_count;
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        EnvScalars *sc = d.sc + e;
+        const float *wE = d.w + (size_t)e * d.Pp;
+        float *gout = d.gnext + (size_t)e * d.Pp;
+        const int *idx; int cnt;
+        current_batch(d, a, e, sc, idx, cnt);
+        __syncthreads();
+        for (int r = tid; r < B; r += blockDim.x) {
+            const int row = (r < cnt) ? idx[r] : 0;
+            idx_s[r] = row;
+            ys[r] = (r < cnt) ? d.labels[row] : 0;
+        }
+        __syncthreads();
+        const int kq = d.Dp >> 2;
+        for (int i = tid; i < cnt * kq; i += blockDim.x) {
+            const int r = i / kq, c = i - r * kq;
+            cp_async16(Xs + r * XS + 4 * c, d.X + (size_t)idx_s[r] * d.Dp + 4 * c);
+        }
+        cp_async_commit();
+        for (int i = tid; i < D * Cq; i += blockDim.x) {
+            const int k = i / Cq, c = i - k * Cq;
+            Ws[i] = c < C ? wE[k * C + c] : 0.f;
+        }
+        if (tid < THIN_CMAX) bs[tid] = tid < C ? wE[d.P1 + tid] : 0.f;
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- forward: 4 samples per warp pass
+        for (int s0 = warp * 4; s0 < B; s0 += 32) {
+            float acc[4][THIN_CMAX];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < THIN_CMAX; ++c) acc[i][c] = 0.f;
+            const float *x0 = Xs + min(s0, B - 1) * XS, *x1 = Xs + min(s0 + 1, B - 1) * XS;
+            const float *x2 = Xs + min(s0 + 2, B - 1) * XS, *x3 = Xs + min(s0 + 3, B - 1) * XS;
+            for (int k = lane; k < D; k += 32) {
+                const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
+                const float4 *wr = reinterpret_cast<const float4 *>(Ws + k * Cq);
+#pragma unroll
+                for (int q = 0; q < THIN_CMAX / 4; ++q) {
+                    if (4 * q < Cq) {
+                        const float4 w4 = wr[q];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc[i][4 * q] = fmaf(xv[i], w4.x, acc[i][4 * q]);
+                            acc[i][4 * q + 1] = fmaf(xv[i], w4.y, acc[i][4 * q + 1]);
+                            acc[i][4 * q + 2] = fmaf(xv[i], w4.z, acc[i][4 * q + 2]);
+                            acc[i][4 * q + 3] = fmaf(xv[i], w4.w, acc[i][4 * q + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < THIN_CMAX; ++c) {
+                    if (c < Cq) {
+                        float v = acc[i][c];
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0 && s0 + i < B) Zs[(s0 + i) * THIN_CMAX + c] = v + bs[c];
+                    }
+                }
+        }
+        __syncthreads();
+        // ---- softmax cross-entropy per sample, dZ in place (problems/optimize_nn.py:47-50)
+        for (int s = tid; s < B; s += blockDim.x) {
+            float *z = Zs + s * THIN_CMAX;
+            float loss = 0.f;
+            if (s < cnt) {
+                const int y = ys[s];
+                float m = z[0];
+                for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+                float sum = 0.f;
+                for (int c = 0; c < C; ++c) sum += expf(z[c] - m);
+                loss = (m + logf(sum)) - z[y];
+                const float inv = 1.0f / sum;
+                for (int c = 0; c < C; ++c) z[c] = expf(z[c] - m) * inv - (c == y ? 1.f : 0.f);
+                for (int c = C; c < THIN_CMAX; ++c) z[c] = 0.f;
+            } else {
+                for (int c = 0; c < THIN_CMAX; ++c) z[c] = 0.f;
+            }
+            lb[s] = loss;
+        }
+        __syncthreads();
+        float loss = 0.f;
+        for (int s = 0; s < cnt; ++s) loss += lb[s];
+        loss /= (float)cnt;
+        // ---- backward: thread = feature k; gradient staged over W (no longer needed)
+        float gsum = 0.f;
+        for (int k = tid; k < D; k += blockDim.x) {
+            float g[THIN_CMAX];
+#pragma unroll
+            for (int c = 0; c < THIN_CMAX; ++c) g[c] = 0.f;
+            for (int s = 0; s < cnt; ++s) {
+                const float x = Xs[s * XS + k];
+                const float4 *dz = reinterpret_cast<const float4 *>(Zs + s * THIN_CMAX);
+#pragma unroll
+                for (int q = 0; q < THIN_CMAX / 4; ++q) {
+                    if (4 * q < Cq) {
+                        const float4 d4 = dz[q];
+                        g[4 * q] = fmaf(x, d4.x, g[4 * q]);
+                        g[4 * q + 1] = fmaf(x, d4.y, g[4 * q + 1]);
+                        g[4 * q + 2] = fmaf(x, d4.z, g[4 * q + 2]);
+                        g[4 * q + 3] = fmaf(x, d4.w, g[4 * q + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < THIN_CMAX; ++c)
+                if (c < C) { Ws[k * C + c] = g[c]; gsum += g[c]; }
+        }
+        __syncthreads();
+        for (int i = tid * 4; i < d.P1; i += blockDim.x * 4) {
+            if (i + 3 < d.P1) *reinterpret_cast<float4 *>(gout + i) = *reinterpret_cast<const float4 *>(Ws + i);
+            else for (int j = i; j < d.P1; ++j) gout[j] = Ws[j];
+        }
+        if (tid < C) {
+            float g = 0.f;
+            for (int s = 0; s < cnt; ++s) g += Zs[s * THIN_CMAX + tid];
+            gout[d.P1 + tid] = g;
+            gsum += g;
+        }
+        if (!SECOND) continue;
+        Stats st;
+        zero_stats(st);
+        st.f[ST_G] = gsum;
+        Totals tot;
+        block_reduce(st, tot, red);
+        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+        __syncthreads();
+        const bool wrap = misc[4] != 0.f;
+        __syncthreads();
+        if (wrap) shuffle_order(d, e, sc);
+    }
+}
+
 // w_t = w_{t-1} - g0 * lr(action)  (multioptlrs.py:86-87), adjusted-weight ring, statistics.
 constexpr int UPD_QUADS = 4;                      // float4 groups per thread
 constexpr int UPD_SEG = 256 * UPD_QUADS * 4;      // parameters per CTA
@@ -2564,6 +2727,8 @@ struct b2e_env {
     size_t smem_obs;
     int chunk_envs, obs_grid;
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
+    bool use_thin;                   // softmax regression: thin_eval_kernel
+    size_t smem_thin;
     float *w2, *g2, *ws;
     int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
     size_t smem_obs2;
@@ -2745,7 +2910,10 @@ int configure(b2e_handle h) {
     // large problems run as a pipeline of kernels (eval / update / eval / observations)
     h->use_eval_kernel = d.fast && d.nks * d.B * d.N1p <= 2 * round_up(d.KT, 4) * d.N1p;
     if (d.generic) { h->use_eval_kernel = false; d.fast = 0; }
-    d.split = (c.env_kind == B2E_ENV_MULTIOPTIMIZE || h->use_eval_kernel || d.generic) ? 1 : 0;
+    h->smem_thin = (size_t)(d.B * d.Ds + d.D * ((d.C + 3) & ~3) + THIN_CMAX + d.B * THIN_CMAX + 3 * d.B + 8) * sizeof(float);
+    h->use_thin = !d.generic && !h->use_eval_kernel && d.kind == B2E_PROBLEM_SOFTMAX && !d.hidden &&
+                  d.C <= THIN_CMAX && d.P >= 4096 && h->smem_thin <= 200 * 1024;
+    d.split = (c.env_kind == B2E_ENV_MULTIOPTIMIZE || h->use_eval_kernel || h->use_thin || d.generic) ? 1 : 0;
     // shared memory carve-up (float offsets, all multiples of 4)
     d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
     int off = d.B * d.Ds + d.xslack;
@@ -2777,7 +2945,7 @@ int configure(b2e_handle h) {
     h->smem_bytes = (size_t)off * sizeof(float);
     if (!d.generic && h->smem_bytes > 227 * 1024 && d.kind == B2E_PROBLEM_SOFTMAX) {
         d.generic = 1; d.fast = 0; d.split = 1;               // does not fit the fused kernel
-        h->use_eval_kernel = false;
+        h->use_eval_kernel = h->use_thin = false;
     }
     if (d.generic) {
         h->smem_bytes = 0;
@@ -2990,6 +3158,18 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
                                  (int)h->smem_obs2) != cudaSuccess)
             return bail("b2e_create: observation kernel (batched gathers) does not fit shared memory");
     }
+    if (h->use_thin) {
+        if (cudaFuncSetAttribute(thin_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_thin) != cudaSuccess ||
+            cudaFuncSetAttribute(thin_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_thin) != cudaSuccess)
+            return bail("b2e_create: thin eval kernel does not fit shared memory");
+        int occ_ev = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, thin_eval_kernel<true>, 256, h->smem_thin) !=
+                cudaSuccess || occ_ev < 1)
+            return bail("b2e_create: thin eval kernel does not fit an SM");
+        h->eval_grid = occ_ev * h->num_sms;
+    }
     if (h->use_eval_kernel) {
         if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess ||
@@ -3149,6 +3329,11 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
+        } else if (h->use_thin) {
+            const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
+            thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
+            h->launches++;
+            CUDA_TRY(h, cudaGetLastError());
         } else {
             StepArgs b = a;
             b.mode = MODE_EVAL_STEP;
@@ -3180,6 +3365,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     mark(0);
     if (h->use_eval_kernel) {
         eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    } else if (h->use_thin) {
+        thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
     } else {                                                 // generic dense stack
         StepArgs b = a;
         b.mode = MODE_EVAL_FIRST;
@@ -3191,6 +3378,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     mark(2);
     if (h->use_eval_kernel) {
         eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    } else if (h->use_thin) {
+        thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
     } else {
         StepArgs b = a;
         b.mode = MODE_EVAL_STEP;

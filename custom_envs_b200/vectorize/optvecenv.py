@@ -103,11 +103,24 @@ class DeviceOptVecEnv(VecEnv):
         self._rew_host = torch.empty(envs, dtype=torch.float32, **pin)
         self._done_host = torch.empty(envs, dtype=torch.uint8, **pin)
         self._info_host = torch.empty((envs, 16), dtype=torch.float64, **pin)
+        # the VecEnv surface repeats reward / done once per agent row (optvecenv.py:43-45); at
+        # 2e8 rows that is cheaper as a device expand + PCIe copy than as np.repeat on the host
+        self._rew_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        self._done_rows = torch.empty(rows, dtype=torch.bool, device=dev)
+        self._rew_rows_host = torch.empty(rows, dtype=torch.float32, **pin)
+        self._done_rows_host = torch.empty(rows, dtype=torch.bool, **pin)
         self._event = torch.cuda.Event()
 
     def _states(self):
         states = self._obs_host.numpy()
         return states.copy() if self.copy_outputs else states
+
+    def _row_outputs(self):
+        """(rewards[rows], terminals[rows]): views of pinned buffers unless copy_outputs."""
+        rewards, terminals = self._rew_rows_host.numpy(), self._done_rows_host.numpy()
+        if self.copy_outputs:
+            return rewards.copy(), terminals.copy()
+        return rewards, terminals
 
     def reset(self):
         obs = self.env.reset()
@@ -116,15 +129,20 @@ class DeviceOptVecEnv(VecEnv):
         return self._states()
 
     def step_async(self, actions):
-        actions = np.asarray(actions, np.float32).reshape(-1)
+        actions = np.ascontiguousarray(np.asarray(actions, np.float32).reshape(-1))
         assert actions.size == self.num_envs
-        self._act_host.numpy()[:] = actions
+        self._act_host.copy_(self._torch.from_numpy(actions))        # multi-threaded host copy
         self._act_dev.copy_(self._act_host, non_blocking=True)
         obs, reward, done, info = self.env.step(self._act_dev)
-        self._obs_host.copy_(obs, non_blocking=True)
+        envs, agents = self.env.num_envs, self.env.num_params
+        self._rew_rows.view(envs, agents).copy_(reward[:, None].expand(envs, agents))
+        self._done_rows.view(envs, agents).copy_(done[:, None].expand(envs, agents))
         self._rew_host.copy_(reward, non_blocking=True)
         self._done_host.copy_(done, non_blocking=True)
         self._info_host.copy_(info, non_blocking=True)
+        self._rew_rows_host.copy_(self._rew_rows, non_blocking=True)
+        self._done_rows_host.copy_(self._done_rows, non_blocking=True)
+        self._obs_host.copy_(obs, non_blocking=True)
         self._event.record(self._torch.cuda.current_stream(self.env.device))
         self.waiting = True
 
@@ -133,8 +151,7 @@ class DeviceOptVecEnv(VecEnv):
         self.waiting = False
         agents = self.env.num_params
         states = self._states()
-        rewards = np.repeat(self._rew_host.numpy(), agents)
-        terminals = np.repeat(self._done_host.numpy().astype(bool), agents)
+        rewards, terminals = self._row_outputs()
         infos = LazyInfos(self._info_host.numpy().copy(), agents)
         for callback in self.callbacks:
             callback(states, rewards, terminals, infos)
@@ -302,8 +319,7 @@ class OptVecEnv(VecEnv):
                 overrides[e] = info
                 if done:
                     env.reset()
-            rewards = np.repeat(reward_env, agents)
-            terminals = np.repeat(done_env, agents)
+            rewards, terminals = impl._row_outputs()
             infos = LazyInfos(info_array, agents, overrides)
         for callback in self.callbacks:
             callback(states, rewards, terminals, infos)
