@@ -31,7 +31,7 @@ constexpr int B_F = (B / 8) * SBO_FB;
 constexpr int A_B = (MT / 8) * SBO_BA;
 constexpr int STAGE = 2 * A_F + 2 * B_F;              // 43264 >= 2 * A_B = 33280
 constexpr int DP_B = (N1 / 8) * SBO_BB;               // dP operand bytes, one of hi/lo
-constexpr int SMEM = 2 * STAGE + 2 * DP_B + 2 * B * N1 * 4 + 1024;
+constexpr int SMEM = STAGE + 2 * DP_B + 2 * B * N1 * 4 + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -88,19 +88,20 @@ struct Args {
     int E, m64_mode;     // m64_mode: TMEM row->lane rule for M = 64 (0: lane = 32*(j/16) + j%16, 1: lane = j)
 };
 
-__global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
+struct Pre { float4 w[4]; float4 x[2]; };          // one tile of global loads held in registers
+
+__global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bar_stage[2];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int idx_s[B];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char *stage[2] = {smem, smem + STAGE};
-    unsigned char *dPhi = smem + 2 * STAGE, *dPlo = dPhi + DP_B;
-    float *Hs = reinterpret_cast<float *>(dPlo + DP_B);          // [B][N1]
+    unsigned char *stg = smem;                                    // ONE operand stage; two CTAs per SM overlap
+    unsigned char *dPhi = smem + STAGE, *dPlo = dPhi + DP_B;
+    float *Hs = reinterpret_cast<float *>(dPlo + DP_B);           // [B][N1]
     float *dPs = Hs + B * N1;                                     // [B][N1] row-major input
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_stage[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_stage[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -111,39 +112,65 @@ __global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    uint32_t uses[2] = {0, 0};                        // completed phases of each stage barrier (uniform)
-    // instruction descriptors: fp32 accumulate, tf32 operands
+    uint32_t ncommit = 0;                             // commits issued so far (uniform)
     const uint32_t idesc_f = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(B >> 3) << 17) | ((uint32_t)(N1 >> 4) << 24);
     const uint32_t idesc_b = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
-    const int r8 = lane & 7, q4 = lane >> 3;          // staging: 8 rows x 4 sixteen-byte groups per warp pass
+    const int r8 = lane & 7, q4 = lane >> 3;
+    unsigned char *FAhi = stg, *FAlo = FAhi + A_F, *FBhi = FAlo + A_F, *FBlo = FBhi + B_F;
+    unsigned char *BAhi = stg, *BAlo = BAhi + A_B;
 
     for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
         const float *We = a.W + (size_t)e * D * N1;
+        __syncthreads();
         if (tid < B) idx_s[tid] = a.idx[(size_t)e * B + tid];
         for (int i = tid; i < B * N1; i += 256) dPs[i] = a.dP[(size_t)e * B * N1 + i];
         __syncthreads();
-        // ================= forward: D[j][s] (M = 64 hidden, N = 32 samples), K = features
-        for (int t = 0; t < NT_F; ++t) {
-            const int b = t & 1, f0 = t * KT;
-            if (t >= 2) { mbar_wait(&bar_stage[b], (uses[b] - 1) & 1); }      // MMAs of tile t-2 done
-            unsigned char *Ahi = stage[b], *Alo = Ahi + A_F, *Bhi = Alo + A_F, *Blo = Bhi + B_F;
-            // W tile -> A operand (M = hidden j, K = feature f): thread = 4 features x 4 hidden units
+        Pre pre;
+        auto load_fwd = [&](int t) {
+            const int f0 = t * KT;
             if (tid < (KT / 4) * (N1 / 4)) {
                 const int jq = tid & 15, f4 = tid >> 4;
-                float4 v[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    v[i] = *reinterpret_cast<const float4 *>(We + (size_t)(f0 + 4 * f4 + i) * N1 + 4 * jq);
-                split_store_t(Ahi, Alo, (jq >> 1) * SBO_FA + f4 * 128 + (jq & 1) * 64, v);
+                    pre.w[i] = *reinterpret_cast<const float4 *>(We + (size_t)(f0 + 4 * f4 + i) * N1 + 4 * jq);
             }
-            // X tile -> B operand (N = sample s, K = feature f): core (s/8, f/4) = 8 samples x 16 bytes
-            for (int c = warp; c < 4 * 4; c += 8) {
-                const int sg = c >> 2, f4 = (c & 3) * 4 + q4;
-                if (f4 < KT / 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[sg * 8 + r8] * D + f0 + 4 * f4);
-                    split_store(Bhi, Blo, sg * SBO_FB + f4 * 128 + r8 * 16, v);
-                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = warp + 8 * u, sg = c >> 2, f4 = (c & 3) * 4 + q4;
+                if (f4 < KT / 4)
+                    pre.x[u] = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[sg * 8 + r8] * D + f0 + 4 * f4);
             }
+        };
+        auto store_fwd = [&]() {
+            if (tid < (KT / 4) * (N1 / 4)) {
+                const int jq = tid & 15, f4 = tid >> 4;
+                split_store_t(FAhi, FAlo, (jq >> 1) * SBO_FA + f4 * 128 + (jq & 1) * 64, pre.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = warp + 8 * u, sg = c >> 2, f4 = (c & 3) * 4 + q4;
+                if (f4 < KT / 4) split_store(FBhi, FBlo, sg * SBO_FB + f4 * 128 + r8 * 16, pre.x[u]);
+            }
+        };
+        auto load_bwd = [&](int m) {
+            const int f0 = m * MT, f4 = tid & 31, sq = tid >> 5;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pre.w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f0 + 4 * f4 < D)
+                    pre.w[i] = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[4 * sq + i] * D + f0 + 4 * f4);
+            }
+        };
+        auto store_bwd = [&]() {
+            const int f4 = tid & 31, sq = tid >> 5;
+            split_store_t(BAhi, BAlo, (f4 >> 1) * SBO_BA + sq * 128 + (f4 & 1) * 64, pre.w);
+        };
+        auto wait_mma = [&]() { if (ncommit) mbar_wait(&bar, (ncommit - 1) & 1); };
+        // ================= forward: D[j][s] (M = 64 hidden, N = 32 samples), K = features
+        load_fwd(0);
+        for (int t = 0; t < NT_F; ++t) {
+            wait_mma();                                           // the stage is free again
+            store_fwd();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -151,35 +178,29 @@ __global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int ks = 0; ks < KT / 8; ++ks) {
                     const uint32_t koff = ks * 256;                          // 8 features = two 16-byte chunks
-                    const uint64_t ah = make_desc(smem_u32(Ahi) + koff, 128, SBO_FA), al = make_desc(smem_u32(Alo) + koff, 128, SBO_FA);
-                    const uint64_t bh = make_desc(smem_u32(Bhi) + koff, 128, SBO_FB), bl = make_desc(smem_u32(Blo) + koff, 128, SBO_FB);
+                    const uint64_t ah = make_desc(smem_u32(FAhi) + koff, 128, SBO_FA), al = make_desc(smem_u32(FAlo) + koff, 128, SBO_FA);
+                    const uint64_t bh = make_desc(smem_u32(FBhi) + koff, 128, SBO_FB), bl = make_desc(smem_u32(FBlo) + koff, 128, SBO_FB);
                     mma_tf32(tmem, al, bh, idesc_f, (t | ks) ? 1u : 0u);
                     mma_tf32(tmem, ah, bl, idesc_f, 1u);
                     mma_tf32(tmem, ah, bh, idesc_f, 1u);
                 }
-                mma_commit(&bar_stage[b]);
+                mma_commit(&bar);
             }
-            uses[b]++;
+            ncommit++;
+            if (t + 1 < NT_F) load_fwd(t + 1); else load_bwd(0);     // in flight while the tensor core works
         }
-        // all forward MMAs done (commits complete in order: the last one covers all)
-        mbar_wait(&bar_stage[(NT_F - 1) & 1], (uses[(NT_F - 1) & 1] - 1) & 1);
-        mbar_wait(&bar_stage[NT_F & 1], (uses[NT_F & 1] - 1) & 1);
+        wait_mma();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {   // Hpre^T from TMEM: row j = hidden unit, 32 columns = samples
-            const int q = warp & 3;
-            int j = -1;
-            if (a.m64_mode == 0) { if (lane < 16) j = q * 16 + lane; } else { if (q < 2) j = q * 32 + lane; }
-            if (warp < 4) {
-                uint32_t v[32];
-                TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (j >= 0)
-                    for (int s = 0; s < B; ++s) Hs[s * N1 + j] = __uint_as_float(v[s]);
+        if (warp < 4) {   // Hpre^T from TMEM: row j = hidden unit -> lane 32*(j/16) + j%16, 32 columns = samples
+            uint32_t v[32];
+            TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (lane < 16) {
+                const int j = warp * 16 + lane;
+#pragma unroll
+                for (int s = 0; s < B; ++s) Hs[s * N1 + j] = __uint_as_float(v[s]);
             }
         }
-        __syncthreads();
-        for (int i = tid; i < B * N1; i += 256) a.H[(size_t)e * B * N1 + i] = Hs[i];
-        // ================= backward: G[f][j] (M = 128 features per tile, N = 64), K = samples
         // dP -> B operand (N = hidden j, K = sample s): thread = 4 samples x 4 hidden units
         if (tid < (B / 4) * (N1 / 4)) {
             const int jq = tid & 15, sq = tid >> 4;
@@ -188,23 +209,13 @@ __global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
             for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4 *>(dPs + (4 * sq + i) * N1 + 4 * jq);
             split_store_t(dPhi, dPlo, (jq >> 1) * SBO_BB + sq * 128 + (jq & 1) * 64, v);
         }
+        __syncthreads();
+        for (int i = tid; i < B * N1; i += 256) a.H[(size_t)e * B * N1 + i] = Hs[i];
+        // ================= backward: G[f][j] (M = 128 features per tile, N = 64), K = samples
         for (int m = 0; m <= NT_B; ++m) {
-            const int b = m & 1, f0 = m * MT;
+            wait_mma();                                           // tile m-1 multiplied: stage free, its accumulator ready
             if (m < NT_B) {
-                if (uses[b] > 0) mbar_wait(&bar_stage[b], (uses[b] - 1) & 1);     // buffer free
-                unsigned char *Ahi = stage[b], *Alo = Ahi + A_B;
-                // X tile -> A operand (M = feature f, K = sample s): thread = 4 samples x 4 features
-                {
-                    const int f4 = tid & 31, sq = tid >> 5;
-                    float4 v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (f0 + 4 * f4 < D)
-                            v[i] = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[4 * sq + i] * D + f0 + 4 * f4);
-                    }
-                    split_store_t(Ahi, Alo, (f4 >> 1) * SBO_BA + sq * 128 + (f4 & 1) * 64, v);
-                }
+                store_bwd();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -212,27 +223,25 @@ __global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
             if (m < NT_B) {
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    unsigned char *Ahi = stage[b], *Alo = Ahi + A_B;
-                    const uint32_t acc = tmem + 64 + 64 * b;
+                    const uint32_t acc = tmem + 64 + 64 * (m & 1);
                     for (int ks = 0; ks < B / 8; ++ks) {
                         const uint32_t koff = ks * 256;                      // 8 samples = two 16-byte chunks
-                        const uint64_t ah = make_desc(smem_u32(Ahi) + koff, 128, SBO_BA), al = make_desc(smem_u32(Alo) + koff, 128, SBO_BA);
+                        const uint64_t ah = make_desc(smem_u32(BAhi) + koff, 128, SBO_BA), al = make_desc(smem_u32(BAlo) + koff, 128, SBO_BA);
                         const uint64_t bh = make_desc(smem_u32(dPhi) + koff, 128, SBO_BB), bl = make_desc(smem_u32(dPlo) + koff, 128, SBO_BB);
                         mma_tf32(acc, al, bh, idesc_b, ks ? 1u : 0u);
                         mma_tf32(acc, ah, bl, idesc_b, 1u);
                         mma_tf32(acc, ah, bh, idesc_b, 1u);
                     }
-                    mma_commit(&bar_stage[b]);
+                    mma_commit(&bar);
                 }
-                uses[b]++;
+                ncommit++;
+                if (m + 1 < NT_B) load_bwd(m + 1);
             }
             if (m >= 1) {   // read out tile m-1 while tile m multiplies
-                const int pb = (m - 1) & 1, pf0 = (m - 1) * MT;
-                mbar_wait(&bar_stage[pb], (uses[pb] - 1 - (pb == b && m < NT_B ? 1 : 0)) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int q = warp & 3, half = warp >> 2;                 // lanes 32q.., columns 32*half..
+                const int pf0 = (m - 1) * MT, q = warp & 3, half = warp >> 2;       // lanes 32q.., columns 32*half..
                 uint32_t v[32];
-                TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16) + 64 + 64 * pb + 32 * half, v);
+                TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16) + 64 + 64 * ((m - 1) & 1) + 32 * half, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int f = pf0 + q * 32 + lane;
                 if (f < D) {
@@ -245,8 +254,8 @@ __global__ void __launch_bounds__(256, 1) tc_fb_kernel(Args a) {
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
     }
+    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
@@ -268,7 +277,7 @@ int main(int argc, char **argv) {
     CHECK(cudaMemset(dH, 0xFF, nP * 4)); CHECK(cudaMemset(dG, 0xFF, nW * 4));
     CHECK(cudaFuncSetAttribute(tc_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     Args a = {dW, dX, didx, ddP, dH, dG, E, m64_mode};
-    const int grid = E < 148 ? E : 148;
+    const int grid = E < 296 ? E : 296;
     tc_fb_kernel<<<grid, 256, SMEM>>>(a);
     CHECK(cudaDeviceSynchronize());
     float *H = (float *)malloc(nP * 4), *G = (float *)malloc(nW * 4);
