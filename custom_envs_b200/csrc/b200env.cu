@@ -1928,6 +1928,336 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
     }
 }
 
+// ------------------------------------------------ tensor-core eval kernel (tcgen05, 3xTF32)
+// The two per-env GEMMs of the one-hidden-layer MLP (BASELINE config 4: D = 784, N1 = 64,
+// B = 32) on the 5th-generation tensor cores:
+//   forward : Hpre^T[j][s] = sum_f W1[f][j] X[s][f]     M = 64 hidden, N = 32 samples, K = D
+//   backward: G[f][j]      = sum_s X[s][f] dPre[s][j]   M = 128 features per tile, N = 64, K = 32
+// fp32 parity (1e-5) is kept with the 3xTF32 split a = hi + lo (hi = the 19 leading bits, which
+// is what the tensor core reads of an fp32 word anyway: profiles/r1_tc_probe.txt):
+// a.b ~ lo.hi + hi.lo + hi.hi, accumulated in fp32 in TMEM; measured error 1.3e-6 of
+// sum|terms| (profiles/r1_tc_fb_probe_v4.txt).  Operands are staged by the threads (global ->
+// registers, one tile ahead -> 4x4 transpose, split -> shared memory) in the K-major
+// no-swizzle canonical layout (core matrix = 8 rows x 16 bytes, K chunks 128 bytes apart,
+// 8-row groups SBO apart; MN-major no-swizzle descriptors do not work for tf32).  One thread
+// issues the MMAs; tcgen05.commit arrives on an mbarrier when the stage may be overwritten.
+// One operand stage per CTA, two CTAs per SM overlap each other.  The tail of the network
+// (bias, relu, second layer, softmax-CE) is the shared-memory code of the FFMA kernels.
+namespace tc {
+constexpr int N1 = 64, B = 32, KT = 56, MT = 128;
+constexpr int SBO_FA = (KT / 4) * 128 + 16;           // forward A = W1^T tile [64 j  x 56 f]
+constexpr int SBO_FB = (KT / 4) * 128;                // forward B = X tile    [32 s  x 56 f]
+constexpr int SBO_BA = (B / 4) * 128 + 16;            // backward A = X^T tile [128 f x 32 s]
+constexpr int SBO_BB = (B / 4) * 128 + 16;            // backward B = dPre^T   [64 j  x 32 s]
+constexpr int A_F = (N1 / 8) * SBO_FA, B_F = (B / 8) * SBO_FB, A_B = (MT / 8) * SBO_BA;
+constexpr int STAGE = 2 * A_F + 2 * B_F;              // 43264 bytes >= 2 * A_B
+constexpr int DP_B = (N1 / 8) * SBO_BB;
+constexpr int OPERAND_BYTES = 2 * STAGE + 2 * DP_B;   // two operand stages + the dPre operand; float region follows
+constexpr int TMEM_COLS = 256;                        // forward 32 columns, backward 2 x 64
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {        // one lane of a converged warp (issues the MMAs)
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void split_store(unsigned char *hi, unsigned char *lo, int off, float4 v) {
+    float4 h, l;
+    // hi = fp32 rounded to nearest at tf32 precision (the tensor core truncates, so the rounding
+    // is done here); lo = exact remainder, |lo| <= 2^-12 |v|
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); l.w = v.w - h.w;
+    *reinterpret_cast<float4 *>(hi + off) = h;
+    *reinterpret_cast<float4 *>(lo + off) = l;
+}
+// 4x4 transpose (rows of v = 4 consecutive K indices, columns = 4 consecutive operand rows)
+__device__ __forceinline__ void split_store_t(unsigned char *hi, unsigned char *lo, int off, const float4 (&v)[4]) {
+    split_store(hi, lo, off, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+    split_store(hi, lo, off + 16, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+    split_store(hi, lo, off + 32, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+    split_store(hi, lo, off + 48, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
+}
+#define B2E_TMEM_LD32(taddr, v) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+                 : "r"(taddr))
+struct Pre { float4 w[4]; float4 x[2]; };            // one tile of global loads held in registers
+}  // namespace tc
+
+template <bool SECOND>
+__global__ void __launch_bounds__(256, 2) tc_eval_kernel(const __grid_constant__ Dev d,
+                                                         const __grid_constant__ StepArgs a) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *sm = reinterpret_cast<float *>(smem_raw);              // Dev offsets (floats) index from here
+    unsigned char *dPhi = smem_raw + 2 * STAGE, *dPlo = dPhi + DP_B;
+    // row-major Hpre / dPre scratch of the tail lives in stage 1 (idle between the two passes);
+    // in the backward pass the same region stages the gradient rows for coalesced stores
+    float *Hb = sm + d.off_H, *dPs = sm + d.off_dP, *misc = sm + d.off_misc;
+    int *idx_s = reinterpret_cast<int *>(sm + d.off_idx);
+    int *ys = reinterpret_cast<int *>(sm + d.off_y);
+    const int D = d.D, NT_F = D / KT, NT_B = (D + MT - 1) / MT;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    uint32_t uses0 = 0, uses1 = 0;                    // commits issued to each stage barrier (uniform)
+    // forward: ONE 128x64x8 MMA per K step, A = [W_hi ; W_lo] rows, B = [X_hi ; X_lo] rows;
+    // backward: x_hi.[dP_hi ; dP_lo] (128x128x8) and x_lo.dP_hi (128x64x8)
+    const uint32_t idesc_f = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * B >> 3) << 17) | ((uint32_t)(2 * N1 >> 4) << 24);
+    const uint32_t idesc_b = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+    const uint32_t idesc_b2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+    const uint64_t stage_step = (uint64_t)(STAGE >> 4);
+    const uint64_t dFA = make_desc(smem_u32(smem_raw), 128, SBO_FA);
+    const uint64_t dFB = make_desc(smem_u32(smem_raw + 2 * A_F), 128, SBO_FB);
+    const uint64_t dBAhi = make_desc(smem_u32(smem_raw), 128, SBO_BA), dBAlo = make_desc(smem_u32(smem_raw + A_B), 128, SBO_BA);
+    const uint64_t dBB = make_desc(smem_u32(dPhi), 128, SBO_BB);
+    const int r8 = lane & 7, q4 = lane >> 3;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto wait_stage = [&](int b) {
+        const uint32_t u = b ? uses1 : uses0;
+        if (u) mbar_wait(&bar[b], (u - 1) & 1);
+    };
+    const int e_end = a.e_begin + a.e_count;
+
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        EnvScalars *sc = d.sc + e;
+        const float *We = d.w + (size_t)e * d.Pp;
+        float *gout = d.gnext + (size_t)e * d.Pp;
+        const int *idx; int cnt;
+        current_batch(d, a, e, sc, idx, cnt);
+        __syncthreads();
+        if (tid < B) {
+            const int row = (tid < cnt) ? idx[tid] : -1;          // ragged last batch: missing rows are zeros
+            idx_s[tid] = row;
+            ys[tid] = row >= 0 ? d.labels[row] : 0;
+        }
+        for (int i = tid; i < d.tailP; i += blockDim.x) sm[d.off_tw + i] = We[d.P1 + i];
+        __syncthreads();
+        Pre pre;
+        auto load_fwd = [&](int t) {
+            const int f0 = t * KT;
+            if (tid < (KT / 4) * (N1 / 4)) {
+                const int jq = tid & 15, f4 = tid >> 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    pre.w[i] = *reinterpret_cast<const float4 *>(We + (size_t)(f0 + 4 * f4 + i) * N1 + 4 * jq);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = warp + 8 * u, sg = c >> 2, f4 = (c & 3) * 4 + q4;
+                if (f4 < KT / 4) {
+                    const int row = idx_s[sg * 8 + r8];
+                    pre.x[u] = row >= 0 ? *reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + f0 + 4 * f4) : zero4;
+                }
+            }
+        };
+        auto store_fwd = [&](int b) {
+            unsigned char *FAhi = smem_raw + b * STAGE, *FAlo = FAhi + A_F, *FBhi = FAlo + A_F, *FBlo = FBhi + B_F;
+            if (tid < (KT / 4) * (N1 / 4)) {
+                const int jq = tid & 15, f4 = tid >> 4;
+                split_store_t(FAhi, FAlo, (jq >> 1) * SBO_FA + f4 * 128 + (jq & 1) * 64, pre.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = warp + 8 * u, sg = c >> 2, f4 = (c & 3) * 4 + q4;
+                if (f4 < KT / 4) split_store(FBhi, FBlo, sg * SBO_FB + f4 * 128 + r8 * 16, pre.x[u]);
+            }
+        };
+        auto load_bwd = [&](int m) {
+            const int f0 = m * MT, f4 = tid & 31, sq = tid >> 5;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = idx_s[4 * sq + i];
+                pre.w[i] = (row >= 0 && f0 + 4 * f4 < D)
+                               ? *reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + f0 + 4 * f4) : zero4;
+            }
+        };
+        auto store_bwd = [&]() {
+            const int f4 = tid & 31, sq = tid >> 5;
+            split_store_t(smem_raw, smem_raw + A_B, (f4 >> 1) * SBO_BA + sq * 128 + (f4 & 1) * 64, pre.w);
+        };
+
+        // ================= forward: two operand stages; accumulators: even K steps at TMEM columns
+        // [0, 64), odd K steps at [64, 128); rows 0..63 = W_hi, 64..127 = W_lo; columns 0..31 = X_hi
+        load_fwd(0);
+        for (int t = 0; t < NT_F; ++t) {
+            const int b = t & 1;
+            wait_stage(b);                                        // MMAs of tile t-2 done: stage b is free
+            store_fwd(b);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warp == 0 && elect_one()) {
+                // the barrier made every thread's st.shared visible to this thread; one proxy fence
+                // orders them before the tensor core's (async proxy) reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t so = b ? stage_step : 0;
+#pragma unroll
+                for (int ks = 0; ks < KT / 8; ++ks) {                        // 8 features = two 16-byte chunks
+                    const uint64_t ko = so + (uint64_t)(ks * 256 >> 4);
+                    mma_tf32(tmem + 64 * (ks & 1), dFA + ko, dFB + ko, idesc_f, (t == 0 && ks < 2) ? 0u : 1u);
+                }
+                mma_commit(&bar[b]);
+            }
+            if (b) uses1++; else uses0++;
+            if (t + 1 < NT_F) load_fwd(t + 1); else load_bwd(0);     // in flight while the tensor core works
+        }
+        wait_stage(0);
+        wait_stage(1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp < 4) {   // M = 128: accumulator row r sits in TMEM lane r
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                         // small products first: X_lo columns, then X_hi
+                const int col = (k < 2 ? 32 : 0) + ((k & 1) ? 0 : 64);
+                uint32_t v[32];
+                B2E_TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16) + col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
+            }
+            const int j = (warp & 1) * 32 + lane;
+            if (warp >= 2) {                                       // W_lo rows: hand the partial sums over
+#pragma unroll
+                for (int s = 0; s < B; ++s) dPs[s * N1 + j] = acc[s];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp < 2) {
+#pragma unroll
+                for (int s = 0; s < B; ++s) Hb[s * N1 + j] = acc[s] + dPs[s * N1 + j];
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ================= tail: bias, relu, second layer, softmax-CE -> dPre [B][N1], tail gradient
+        const float loss = tail_eval(d, sm, cnt);
+        float gsum = 0.f;
+        for (int i = tid; i < d.tailP; i += blockDim.x) {
+            const float g = sm[d.off_tg + i];
+            gout[d.P1 + i] = g;
+            gsum += g;
+        }
+        // dPre -> B operand (N = hidden j, K = sample s): thread = 4 samples x 4 hidden units
+        if (tid < (B / 4) * (N1 / 4)) {
+            const int jq = tid & 15, sq = tid >> 4;
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4 *>(dPs + (4 * sq + i) * N1 + 4 * jq);
+            split_store_t(dPhi, dPlo, (jq >> 1) * SBO_BB + sq * 128 + (jq & 1) * 64, v);
+        }
+        __syncthreads();                                          // the scratch in stage 1 is dead from here
+        // ================= backward: one operand stage (stage 0); accumulators P = x_hi.[dP_hi ; dP_lo]
+        // at TMEM columns [0, 128), Q = x_lo.dP_hi at [128, 192); G = P[:, 0:64] + P[:, 64:128] + Q
+        float *scr = reinterpret_cast<float *>(smem_raw + STAGE) + warp * (32 * 33);
+        auto readout = [&](int m) {
+            wait_stage(0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3, half = warp >> 2;                 // lanes 32q.., columns 32*half.. of each block
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int col = (k == 0 ? 128 : k == 1 ? 64 : 0) + 32 * half;
+                uint32_t v[32];
+                B2E_TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
+            }
+            // lane = feature row; transpose through shared memory so that a warp store covers one row
+#pragma unroll
+            for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = acc[i];
+            __syncwarp();
+            const int fbase = m * MT + q * 32;
+            for (int r = 0; r < 32; ++r) {
+                if (fbase + r < D) {
+                    const float g = scr[r * 33 + lane];
+                    gout[(size_t)(fbase + r) * N1 + 32 * half + lane] = g;
+                    gsum += g;
+                }
+            }
+            __syncwarp();
+        };
+        for (int m = 0; m < NT_B; ++m) {
+            wait_stage(0);                                        // tile m-1 multiplied: stage and accumulators free
+            store_bwd();
+            if (m >= 1) readout(m - 1);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (warp == 0 && elect_one()) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ks = 0; ks < B / 8; ++ks) {                     // 8 samples = two 16-byte chunks
+                    const uint64_t ko = (uint64_t)(ks * 256 >> 4);
+                    mma_tf32(tmem, dBAhi + ko, dBB + ko, idesc_b2, ks ? 1u : 0u);
+                    mma_tf32(tmem + 128, dBAlo + ko, dBB + ko, idesc_b, ks ? 1u : 0u);
+                }
+                mma_commit(&bar[0]);
+            }
+            uses0++;
+            if (m + 1 < NT_B) load_bwd(m + 1);
+        }
+        readout(NT_B - 1);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (!SECOND) continue;
+        // ---- scalars of the step (thread 0): history bookkeeping, reward, done, info
+        __syncthreads();                                          // the reduction scratch shares stage 1
+        Stats st;
+        zero_stats(st);
+        st.f[ST_G] = gsum;
+        Totals tot;
+        block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
+        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+        __syncthreads();
+        const bool wrap = misc[4] != 0.f;
+        __syncthreads();
+        if (wrap) shuffle_order(d, e, sc);
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
 // ------------------------------------------------ thin eval kernel: no hidden layer
 // Softmax regression (BASELINE config 3: 784 -> 10): logits Z = X.W + b with at most 16
 // classes.  There is almost no arithmetic (1 MFLOP per env), the kernel is the minibatch
@@ -2729,6 +3059,10 @@ struct b2e_env {
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
     bool use_thin;                   // softmax regression: thin_eval_kernel
     size_t smem_thin;
+    bool use_tc;                     // tcgen05 eval kernel replaces eval_kernel
+    Dev d_tc;                        // Dev with the tensor-core kernel's shared-memory layout
+    size_t smem_tc;
+    int tc_grid;
     float *w2, *g2, *ws;
     int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
     size_t smem_obs2;
@@ -3006,6 +3340,30 @@ int configure(b2e_handle h) {
         h->smem_eval = (size_t)o * sizeof(float);
         v.split = d.split;
     }
+    {   // tensor-core eval kernel: operand stage first, then the float regions of the tail
+        // opt-in (B2E_TC=1): parity-green, but in the step pipeline it is still slower than the FFMA
+        // eval kernel (1.24 vs 1.12 ms at 4096 envs; profiles/r1_notes.md has the analysis)
+        const char *tcv = getenv("B2E_TC");
+        h->use_tc = h->use_eval_kernel && d.hidden && d.N1 == tc::N1 && d.N1p == tc::N1 && d.B == tc::B &&
+                    d.D % tc::KT == 0 && d.kind == B2E_PROBLEM_SOFTMAX && tcv && atoi(tcv) != 0;
+        h->d_tc = d;
+        Dev &v = h->d_tc;
+        // scratch that only lives between the two passes sits inside operand stage 1
+        int in1 = tc::STAGE / 4;
+        v.off_H = in1; in1 += round_up(d.B * d.N1p, 4);
+        v.off_dP = in1; in1 += round_up(d.B * d.N1p, 4);
+        v.off_Z = in1; in1 += d.hidden ? round_up(d.B * d.Cp, 4) : 0;
+        v.off_lb = in1; in1 += round_up(d.B, 4);
+        v.off_red2 = in1; in1 += 2 * NSTAT * 16;
+        if (in1 > 2 * tc::STAGE / 4) h->use_tc = false;
+        int o = tc::OPERAND_BYTES / 4;
+        v.off_tw = o; o += round_up(d.tailP, 4);
+        v.off_tg = o; o += round_up(d.tailP, 4);
+        v.off_idx = o; o += round_up(d.B, 4);
+        v.off_y = o; o += round_up(d.B, 4);
+        v.off_misc = o; o += 8 + 2 * B2E_MAX_HISTORY;
+        h->smem_tc = (size_t)o * sizeof(float);
+    }
     return 0;
 }
 
@@ -3170,6 +3528,19 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             return bail("b2e_create: thin eval kernel does not fit an SM");
         h->eval_grid = occ_ev * h->num_sms;
     }
+    if (h->use_tc) {
+        if (cudaFuncSetAttribute(tc_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_tc) != cudaSuccess ||
+            cudaFuncSetAttribute(tc_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_tc) != cudaSuccess)
+            return bail("b2e_create: tensor-core eval kernel does not fit shared memory");
+        int occ_tc = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tc, tc_eval_kernel<true>, 256, h->smem_tc) !=
+                cudaSuccess || occ_tc < 1)
+            return bail("b2e_create: tensor-core eval kernel does not fit an SM");
+        if (occ_tc > 512 / tc::TMEM_COLS) occ_tc = 512 / tc::TMEM_COLS;    // TMEM: 512 columns per SM
+        h->tc_grid = occ_tc * h->num_sms;
+    }
     if (h->use_eval_kernel) {
         if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess ||
@@ -3321,12 +3692,14 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
         if (h->use_eval_kernel) {
-            Dev &v = h->d_eval;
+            Dev &v = h->use_tc ? h->d_tc : h->d_eval;
             v.gprev = d.gprev; v.gnext = d.gnext; v.perm_stride = d.perm_stride;
             v.X = d.X; v.labels = d.labels; v.targets = d.targets; v.w = d.w; v.sc = d.sc;
             v.ord = d.ord; v.perm = d.perm;
-            const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
-            eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
+            const int cap = h->use_tc ? h->tc_grid : h->eval_grid;
+            const int grid_ev = d.E < cap ? d.E : cap;
+            if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
+            else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
         } else if (h->use_thin) {
@@ -3352,19 +3725,20 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         return 0;
     }
     // ---- large problems: eval(w) -> update -> eval(w') -> observations, all on the caller's stream
-    {
-        Dev &v = h->d_eval;                                  // same pointers, eval-kernel smem layout
-        v.gprev = d.gprev; v.gnext = d.gnext; v.perm_stride = d.perm_stride;
-        v.X = d.X; v.labels = d.labels; v.targets = d.targets; v.w = d.w; v.sc = d.sc;
-        v.ord = d.ord; v.perm = d.perm; v.part = d.part; v.part_u = d.part_u;
-        v.ringw = d.ringw; v.ringg = d.ringg; v.row_of_param = d.row_of_param; v.param_of_row = d.param_of_row;
-    }
+    Dev &dv = h->use_tc ? h->d_tc : h->d_eval;               // same pointers, eval-kernel smem layout
+    dv.gprev = d.gprev; dv.gnext = d.gnext; dv.perm_stride = d.perm_stride;
+    dv.X = d.X; dv.labels = d.labels; dv.targets = d.targets; dv.w = d.w; dv.sc = d.sc;
+    dv.ord = d.ord; dv.perm = d.perm; dv.part = d.part; dv.part_u = d.part_u;
+    dv.ringw = d.ringw; dv.ringg = d.ringg; dv.row_of_param = d.row_of_param; dv.param_of_row = d.param_of_row;
     a.e_begin = 0; a.e_count = d.E;
-    const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
+    const int cap_ev = h->use_tc ? h->tc_grid : h->eval_grid;
+    const int grid_ev = d.E < cap_ev ? d.E : cap_ev;
     auto mark = [&](int i) { if (h->trace) cudaEventRecord(h->tr[i], main_s); };
     mark(0);
-    if (h->use_eval_kernel) {
-        eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    if (h->use_tc) {
+        tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
+    } else if (h->use_eval_kernel) {
+        eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
         thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
     } else {                                                 // generic dense stack
@@ -3376,8 +3750,10 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     mark(1);
     update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
-    if (h->use_eval_kernel) {
-        eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(h->d_eval, a);
+    if (h->use_tc) {
+        tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
+    } else if (h->use_eval_kernel) {
+        eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
         thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
     } else {

@@ -31,7 +31,7 @@ constexpr int B_F = (B / 8) * SBO_FB;
 constexpr int A_B = (MT / 8) * SBO_BA;
 constexpr int STAGE = 2 * A_F + 2 * B_F;              // 43264 >= 2 * A_B = 33280
 constexpr int DP_B = (N1 / 8) * SBO_BB;               // dP operand bytes, one of hi/lo
-constexpr int SMEM = STAGE + 2 * DP_B + 2 * B * N1 * 4 + 1024;
+constexpr int SMEM = 2 * STAGE + 2 * DP_B + 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -42,6 +42,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t ad, uint64_t bd
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -54,10 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 __device__ __forceinline__ void split_store(unsigned char *hi, unsigned char *lo, int off, float4 v) {
     float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+    // hi = fp32 rounded to nearest at tf32 precision (the tensor core truncates, so rounding is
+    // done here); lo = exact remainder, |lo| <= 2^-12 |v|, its own truncation error is 2^-23 |v|
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); l.w = v.w - h.w;
     *reinterpret_cast<float4 *>(hi + off) = h;
     *reinterpret_cast<float4 *>(lo + off) = l;
 }
@@ -85,23 +92,26 @@ struct Args {
     const float *dP;     // [E][B][N1]
     float *H;            // [E][B][N1]   forward result
     float *G;            // [E][D][N1]   backward result
+    long long *prof;     // clock64() samples of block 0 / thread 0
     int E, m64_mode;     // m64_mode: TMEM row->lane rule for M = 64 (0: lane = 32*(j/16) + j%16, 1: lane = j)
 };
 
 struct Pre { float4 w[4]; float4 x[2]; };          // one tile of global loads held in registers
 
+// v5: two operand stages (the stores of tile t+1 overlap the MMAs of tile t) AND two CTAs per
+// SM: the row-major Hpre / dPre scratch lives inside stage 1, which is idle between the passes.
 __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ int idx_s[B];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char *stg = smem;                                    // ONE operand stage; two CTAs per SM overlap
-    unsigned char *dPhi = smem + STAGE, *dPlo = dPhi + DP_B;
-    float *Hs = reinterpret_cast<float *>(dPlo + DP_B);           // [B][N1]
-    float *dPs = Hs + B * N1;                                     // [B][N1] row-major input
+    unsigned char *dPhi = smem + 2 * STAGE, *dPlo = dPhi + DP_B;
+    float *Hs = reinterpret_cast<float *>(smem + STAGE);          // [B][N1]  (inside stage 1)
+    float *dPs = Hs + B * N1;                                     // [B][N1]
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -112,21 +122,31 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    uint32_t ncommit = 0;                             // commits issued so far (uniform)
-    const uint32_t idesc_f = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(B >> 3) << 17) | ((uint32_t)(N1 >> 4) << 24);
-    const uint32_t idesc_b = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+    uint32_t uses0 = 0, uses1 = 0;                    // commits issued to each stage barrier (uniform)
+    const uint32_t idesc_f = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * B >> 3) << 17) | ((uint32_t)(2 * N1 >> 4) << 24);   // 128 x 64
+    const uint32_t idesc_b = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);        // 128 x 64
+    const uint32_t idesc_b2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * N1 >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);   // 128 x 128
     const int r8 = lane & 7, q4 = lane >> 3;
-    unsigned char *FAhi = stg, *FAlo = FAhi + A_F, *FBhi = FAlo + A_F, *FBlo = FBhi + B_F;
-    unsigned char *BAhi = stg, *BAlo = BAhi + A_B;
+    const uint64_t dBBhi = make_desc(smem_u32(dPhi), 128, SBO_BB), dBBlo = make_desc(smem_u32(dPlo), 128, SBO_BB);
+    const uint64_t stage_step = (uint64_t)(STAGE >> 4);           // descriptor address field step between the stages
+    const uint64_t dFAhi = make_desc(smem_u32(smem), 128, SBO_FA), dFAlo = make_desc(smem_u32(smem + A_F), 128, SBO_FA);
+    const uint64_t dFBhi = make_desc(smem_u32(smem + 2 * A_F), 128, SBO_FB), dFBlo = make_desc(smem_u32(smem + 2 * A_F + B_F), 128, SBO_FB);
+    const uint64_t dBAhi = make_desc(smem_u32(smem), 128, SBO_BA), dBAlo = make_desc(smem_u32(smem + A_B), 128, SBO_BA);
+    auto wait_stage = [&](int b) {
+        const uint32_t u = b ? uses1 : uses0;
+        if (u) mbar_wait(&bar[b], (u - 1) & 1);
+    };
 
+    int pi = 0;
+#define PROF() do { if (a.prof && blockIdx.x == 0 && tid == 0 && e == (int)gridDim.x && pi < 256) a.prof[pi++] = clock64(); } while (0)
     for (int e = blockIdx.x; e < a.E; e += gridDim.x) {
         const float *We = a.W + (size_t)e * D * N1;
         __syncthreads();
         if (tid < B) idx_s[tid] = a.idx[(size_t)e * B + tid];
-        for (int i = tid; i < B * N1; i += 256) dPs[i] = a.dP[(size_t)e * B * N1 + i];
         __syncthreads();
-        Pre pre;
+        Pre pre = {};
         auto load_fwd = [&](int t) {
+            if (a.m64_mode == 1) return;                          // timing experiment: no global loads
             const int f0 = t * KT;
             if (tid < (KT / 4) * (N1 / 4)) {
                 const int jq = tid & 15, f4 = tid >> 4;
@@ -141,7 +161,8 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
                     pre.x[u] = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[sg * 8 + r8] * D + f0 + 4 * f4);
             }
         };
-        auto store_fwd = [&]() {
+        auto store_fwd = [&](int b) {
+            unsigned char *FAhi = smem + b * STAGE, *FAlo = FAhi + A_F, *FBhi = FAlo + A_F, *FBlo = FBhi + B_F;
             if (tid < (KT / 4) * (N1 / 4)) {
                 const int jq = tid & 15, f4 = tid >> 4;
                 split_store_t(FAhi, FAlo, (jq >> 1) * SBO_FA + f4 * 128 + (jq & 1) * 64, pre.w);
@@ -153,6 +174,7 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
             }
         };
         auto load_bwd = [&](int m) {
+            if (a.m64_mode == 1) return;
             const int f0 = m * MT, f4 = tid & 31, sq = tid >> 5;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -161,46 +183,79 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
                     pre.w[i] = *reinterpret_cast<const float4 *>(a.X + (size_t)idx_s[4 * sq + i] * D + f0 + 4 * f4);
             }
         };
-        auto store_bwd = [&]() {
+        auto store_bwd = [&](int b) {
+            unsigned char *BAhi = smem + b * STAGE, *BAlo = BAhi + A_B;
             const int f4 = tid & 31, sq = tid >> 5;
             split_store_t(BAhi, BAlo, (f4 >> 1) * SBO_BA + sq * 128 + (f4 & 1) * 64, pre.w);
         };
-        auto wait_mma = [&]() { if (ncommit) mbar_wait(&bar, (ncommit - 1) & 1); };
         // ================= forward: D[j][s] (M = 64 hidden, N = 32 samples), K = features
+        PROF();
         load_fwd(0);
         for (int t = 0; t < NT_F; ++t) {
-            wait_mma();                                           // the stage is free again
-            store_fwd();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int b = t & 1;
+            PROF();
+            wait_stage(b);                                        // MMAs of tile t-2 done: stage b is free
+            PROF();
+            store_fwd(b);
+            PROF();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
+                // the barrier made every thread's st.shared visible to this thread; ONE proxy fence
+                // here orders them before the tensor core's (async proxy) reads.  A fence in every
+                // thread would also wait for that thread's prefetched global loads.
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int ks = 0; ks < KT / 8; ++ks) {
-                    const uint32_t koff = ks * 256;                          // 8 features = two 16-byte chunks
-                    const uint64_t ah = make_desc(smem_u32(FAhi) + koff, 128, SBO_FA), al = make_desc(smem_u32(FAlo) + koff, 128, SBO_FA);
-                    const uint64_t bh = make_desc(smem_u32(FBhi) + koff, 128, SBO_FB), bl = make_desc(smem_u32(FBlo) + koff, 128, SBO_FB);
-                    mma_tf32(tmem, al, bh, idesc_f, (t | ks) ? 1u : 0u);
-                    mma_tf32(tmem, ah, bl, idesc_f, 1u);
-                    mma_tf32(tmem, ah, bh, idesc_f, 1u);
+                const uint64_t so = b ? stage_step : 0;
+                // A = [W_hi ; W_lo] (128 rows) and B = [X_hi ; X_lo] (64 rows) are adjacent in shared
+                // memory with uniform row-group strides, so ONE 128x64x8 MMA per K step yields all four
+                // split products: D[0:64,0:32] hi.hi, D[0:64,32:64] hi.lo, D[64:128,0:32] lo.hi,
+                // D[64:128,32:64] lo.lo.  Even / odd K steps use separate accumulators.
+#pragma unroll
+                for (int ks = 0; ks < KT / 8; ++ks) {                        // 8 features = two 16-byte chunks
+                    const uint64_t ko = so + (uint64_t)(ks * 256 >> 4);
+                    mma_tf32(tmem + 64 * (ks & 1), dFAhi + ko, dFBhi + ko, idesc_f, (t == 0 && ks < 2) ? 0u : 1u);
                 }
-                mma_commit(&bar);
+                mma_commit(&bar[b]);
             }
-            ncommit++;
+            PROF();
+            if (b) uses1++; else uses0++;
             if (t + 1 < NT_F) load_fwd(t + 1); else load_bwd(0);     // in flight while the tensor core works
         }
-        wait_mma();
+        PROF();
+        wait_stage(0);
+        wait_stage(1);
+        PROF();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (warp < 4) {   // Hpre^T from TMEM: row j = hidden unit -> lane 32*(j/16) + j%16, 32 columns = samples
-            uint32_t v[32];
-            TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (lane < 16) {
-                const int j = warp * 16 + lane;
+        if (warp < 4) {   // M = 128: accumulator row r sits in TMEM lane r; rows 0..63 = W_hi.X, 64..127 = W_lo.X
+            float acc[32];
 #pragma unroll
-                for (int s = 0; s < B; ++s) Hs[s * N1 + j] = __uint_as_float(v[s]);
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                         // (x_lo, odd K), (x_lo, even K), (x_hi, odd), (x_hi, even)
+                const int col = (k < 2 ? 32 : 0) + ((k & 1) ? 0 : 64);
+                uint32_t v[32];
+                TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16) + col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
             }
+            const int j = (warp & 1) * 32 + lane;
+            if (warp >= 2) {                                       // W_lo rows: hand the partial sums over
+#pragma unroll
+                for (int s = 0; s < B; ++s) dPs[s * N1 + j] = acc[s];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp < 2) {
+#pragma unroll
+                for (int s = 0; s < B; ++s) Hs[s * N1 + j] = acc[s] + dPs[s * N1 + j];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        __syncthreads();
+        for (int i = tid; i < B * N1; i += 256) dPs[i] = a.dP[(size_t)e * B * N1 + i];
+        __syncthreads();
+        for (int i = tid; i < B * N1; i += 256) a.H[(size_t)e * B * N1 + i] = Hs[i];
         // dP -> B operand (N = hidden j, K = sample s): thread = 4 samples x 4 hidden units
         if (tid < (B / 4) * (N1 / 4)) {
             const int jq = tid & 15, sq = tid >> 4;
@@ -209,50 +264,61 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
             for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4 *>(dPs + (4 * sq + i) * N1 + 4 * jq);
             split_store_t(dPhi, dPlo, (jq >> 1) * SBO_BB + sq * 128 + (jq & 1) * 64, v);
         }
-        __syncthreads();
-        for (int i = tid; i < B * N1; i += 256) a.H[(size_t)e * B * N1 + i] = Hs[i];
+        __syncthreads();                                          // scratch in stage 1 is dead from here
         // ================= backward: G[f][j] (M = 128 features per tile, N = 64), K = samples
-        for (int m = 0; m <= NT_B; ++m) {
-            wait_mma();                                           // tile m-1 multiplied: stage free, its accumulator ready
-            if (m < NT_B) {
-                store_bwd();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        float *scr = reinterpret_cast<float *>(smem + STAGE) + warp * (32 * 33);   // stage 1 is idle in this pass
+        auto readout = [&](int m) {                               // G rows of tile m: P[:,0:64] + P[:,64:128] + Q
+            wait_stage(0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3, half = warp >> 2;                 // lanes 32q.., columns 32*half.. of each block
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                             // x_lo.dP_hi, x_hi.dP_lo, x_hi.dP_hi
+                const int col = (k == 0 ? 128 : k == 1 ? 64 : 0) + 32 * half;
+                uint32_t v[32];
+                TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16) + col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
             }
+            // lane = feature row; transpose through shared memory so that a warp store covers one row
+#pragma unroll
+            for (int i = 0; i < 32; ++i) scr[lane * 33 + i] = acc[i];
+            __syncwarp();
+            const int fbase = m * MT + q * 32;
+            for (int r = 0; r < 32; ++r)
+                if (fbase + r < D) a.G[((size_t)e * D + fbase + r) * N1 + 32 * half + lane] = scr[r * 33 + lane];
+            __syncwarp();
+        };
+        PROF();
+        for (int m = 0; m < NT_B; ++m) {
+            PROF();
+            wait_stage(0);                                        // tile m-1 multiplied: stage and accumulators free
+            store_bwd(0);
+            PROF();
+            if (m >= 1) readout(m - 1);
+            PROF();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
-            if (m < NT_B) {
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t acc = tmem + 64 + 64 * (m & 1);
-                    for (int ks = 0; ks < B / 8; ++ks) {
-                        const uint32_t koff = ks * 256;                      // 8 samples = two 16-byte chunks
-                        const uint64_t ah = make_desc(smem_u32(BAhi) + koff, 128, SBO_BA), al = make_desc(smem_u32(BAlo) + koff, 128, SBO_BA);
-                        const uint64_t bh = make_desc(smem_u32(dPhi) + koff, 128, SBO_BB), bl = make_desc(smem_u32(dPlo) + koff, 128, SBO_BB);
-                        mma_tf32(acc, al, bh, idesc_b, ks ? 1u : 0u);
-                        mma_tf32(acc, ah, bl, idesc_b, 1u);
-                        mma_tf32(acc, ah, bh, idesc_b, 1u);
-                    }
-                    mma_commit(&bar);
-                }
-                ncommit++;
-                if (m + 1 < NT_B) load_bwd(m + 1);
-            }
-            if (m >= 1) {   // read out tile m-1 while tile m multiplies
+            if (warp == 0 && elect_one()) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int pf0 = (m - 1) * MT, q = warp & 3, half = warp >> 2;       // lanes 32q.., columns 32*half..
-                uint32_t v[32];
-                TMEM_LD32(tmem + ((uint32_t)(q * 32) << 16) + 64 + 64 * ((m - 1) & 1) + 32 * half, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int f = pf0 + q * 32 + lane;
-                if (f < D) {
-                    float4 *dst = reinterpret_cast<float4 *>(a.G + ((size_t)e * D + f) * N1 + 32 * half);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                for (int ks = 0; ks < B / 8; ++ks) {                     // 8 samples = two 16-byte chunks
+                    const uint64_t ko = (uint64_t)(ks * 256 >> 4);
+                    mma_tf32(tmem, dBAhi + ko, dBBhi + ko, idesc_b2, ks ? 1u : 0u);          // x_hi.[dP_hi ; dP_lo]
+                    mma_tf32(tmem + 128, dBAlo + ko, dBBhi + ko, idesc_b, ks ? 1u : 0u);     // x_lo.dP_hi
                 }
+                mma_commit(&bar[0]);
             }
+            uses0++;
+            if (m + 1 < NT_B) load_bwd(m + 1);
         }
+        PROF();
+        readout(NT_B - 1);
+        PROF();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -260,7 +326,7 @@ __global__ void __launch_bounds__(256, 2) tc_fb_kernel(Args a) {
 }
 
 int main(int argc, char **argv) {
-    const int E = argc > 1 ? atoi(argv[1]) : 592, rows = 4096, m64_mode = argc > 2 ? atoi(argv[2]) : 0;
+    const int E = argc > 1 ? atoi(argv[1]) : 592, rows = argc > 2 ? atoi(argv[2]) : 4096, m64_mode = argc > 3 ? atoi(argv[3]) : 0;
     size_t nW = (size_t)E * D * N1, nX = (size_t)rows * D, nP = (size_t)E * B * N1;
     float *W = (float *)malloc(nW * 4), *X = (float *)malloc(nX * 4), *dP = (float *)malloc(nP * 4);
     int *idx = (int *)malloc((size_t)E * B * 4);
@@ -276,7 +342,8 @@ int main(int argc, char **argv) {
     CHECK(cudaMemcpy(ddP, dP, nP * 4, cudaMemcpyHostToDevice)); CHECK(cudaMemcpy(didx, idx, (size_t)E * B * 4, cudaMemcpyHostToDevice));
     CHECK(cudaMemset(dH, 0xFF, nP * 4)); CHECK(cudaMemset(dG, 0xFF, nW * 4));
     CHECK(cudaFuncSetAttribute(tc_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    Args a = {dW, dX, didx, ddP, dH, dG, E, m64_mode};
+    long long *dprof; CHECK(cudaMalloc(&dprof, 256 * 8)); CHECK(cudaMemset(dprof, 0, 256 * 8));
+    Args a = {dW, dX, didx, ddP, dH, dG, dprof, E, m64_mode};
     const int grid = E < 296 ? E : 296;
     tc_fb_kernel<<<grid, 256, SMEM>>>(a);
     CHECK(cudaDeviceSynchronize());
@@ -298,6 +365,11 @@ int main(int argc, char **argv) {
         }
     }
     printf("E=%d m64_mode=%d: forward max err / sum|terms| = %.3e, backward = %.3e (fp32 FFMA would be ~1e-7)\n", E, m64_mode, eh, eg);
+    {   long long hp[256]; CHECK(cudaMemcpy(hp, dprof, 256 * 8, cudaMemcpyDeviceToHost));
+        printf("clock64 deltas (cycles) of block 0 / thread 0, second env:\n");
+        for (int i = 1; i < 256 && hp[i]; ++i) printf("%lld%s", hp[i] - hp[i - 1], (i % 16) ? " " : "\n");
+        printf("\n");
+        a.prof = nullptr; }
     cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(t0);

@@ -138,7 +138,7 @@ def test_loss_and_gradient_match_oracle(name):
     env.close()
 
 
-@pytest.mark.parametrize('row_order', ['lexicographic', 'natural', 'lexicographic-generic'])
+@pytest.mark.parametrize('row_order', ['lexicographic', 'natural', 'lexicographic-generic', 'natural-tc'])
 @pytest.mark.parametrize('name', list(SPECS))
 def test_step_parity_from_identical_states(name, row_order, monkeypatch):
     """Per-step parity with host-supplied minibatch indices (external index mode).
@@ -146,6 +146,12 @@ def test_step_parity_from_identical_states(name, row_order, monkeypatch):
     also cover, so both implementations are held to the same oracle."""
     BatchedOptEnv, _ = _mods()
     spec, num_rows, batch, num_envs = SPECS[name]
+    if row_order.endswith('-tc'):
+        # the opt-in tcgen05 (3xTF32) eval kernel, held to the same oracle and tolerances
+        if name != 'mlp_784x64x10':
+            pytest.skip('the tensor-core eval kernel covers the config-4 shape')
+        monkeypatch.setenv('B2E_TC', '1')
+        row_order = 'natural'
     if row_order.endswith('-generic'):
         if spec.kind != 'softmax' or name in ('mlp_784x64x10', 'softmax_784x10') or len(spec.hidden) > 1:
             pytest.skip('generic path: softmax stacks; large / already-generic specs run it elsewhere')
