@@ -398,23 +398,28 @@ __device__ void g_compute(const Dev &d, const float *sm, float *T, int k0, int c
 // backward: thread = 4 rows x 8 columns of the tile, all samples.
 // A thread's 8 columns are two runs of 4, N1/2 apart, so that a warp's float4 accesses
 // cover whole 128-byte lines.
+// CN1 > 0 fixes the layer width (and B = 32, 256 threads) at compile time so that the strides
+// become immediates; CN1 = 0 reads them from the Dev.
+template <int CN1 = 0>
 __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xbase, int xstride,
                                                   const float *T, int krows4, float (&acc)[4][8]) {
     const int t = threadIdx.x;
-    const int per_slice = 8 * d.cg;                       // threads per K slice
+    const int N1 = CN1 ? CN1 : d.N1, N1p = CN1 ? CN1 : d.N1p, cg = CN1 ? CN1 / 8 : d.cg;
+    const int nB = CN1 ? 32 : d.B, nthreads = CN1 ? 256 : (int)blockDim.x;
+    const int per_slice = 8 * cg;                         // threads per K slice
     const int q = t / per_slice, u = t - q * per_slice;
-    const int sg = u / d.cg, cgi = u - sg * d.cg;
-    const int nslices = blockDim.x / per_slice;
+    const int sg = u / cg, cgi = u - sg * cg;
+    const int nslices = nthreads / per_slice;
     const int rows_per = ((krows4 / 4 + nslices - 1) / nslices) * 4;
     const int kb = q * rows_per;
     int ke = kb + rows_per;
     ke = ke < krows4 ? ke : krows4;
-    const int half = d.N1 >> 1;
+    const int half = N1 >> 1;
     const float *xr[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int s = sg + 8 * i;
-        s = s < d.B ? s : d.B - 1;
+        s = s < nB ? s : nB - 1;
         xr[i] = xbase + s * xstride;
     }
     const float *tc = T + 4 * cgi;
@@ -427,7 +432,7 @@ __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xba
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const float *tr = tc + (k + kk) * d.N1p;
+            const float *tr = tc + (k + kk) * N1p;
             const float4 t0 = *reinterpret_cast<const float4 *>(tr);
             const float4 t1 = *reinterpret_cast<const float4 *>(tr + half);
 #pragma unroll
@@ -446,27 +451,30 @@ __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xba
     }
 }
 
-__device__ void f_store_fast(const Dev &d, float *sm, float (&acc)[4][8]) {
+template <int CN1 = 0>
+__device__ __forceinline__ void f_store_fast(const Dev &d, float *sm, float (&acc)[4][8]) {
     const int t = threadIdx.x;
-    const int per_slice = 8 * d.cg;
+    const int N1 = CN1 ? CN1 : d.N1, N1p = CN1 ? CN1 : d.N1p, cg = CN1 ? CN1 / 8 : d.cg;
+    const int nB = CN1 ? 32 : d.B, nthreads = CN1 ? 256 : (int)blockDim.x;
+    const int per_slice = 8 * cg;
     const int q = t / per_slice, u = t - q * per_slice;
-    const int sg = u / d.cg, cgi = u - sg * d.cg;
-    const int nslices = blockDim.x / per_slice;
-    const int half = d.N1 >> 1;
+    const int sg = u / cg, cgi = u - sg * cg;
+    const int nslices = nthreads / per_slice;
+    const int half = N1 >> 1;
     float *Hb = sm + d.off_H;
     float *red = sm + d.off_red;
-    const int n = d.B * d.N1p;
+    const int n = nB * N1p;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int s = sg + 8 * i;
-        if (s < d.B) {
-            float *dst = red + (size_t)q * n + s * d.N1p + 4 * cgi;
+        if (s < nB) {
+            float *dst = red + (size_t)q * n + s * N1p + 4 * cgi;
             *reinterpret_cast<float4 *>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
             *reinterpret_cast<float4 *>(dst + half) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         }
     }
     __syncthreads();
-    for (int i = t; i < n; i += blockDim.x) {
+    for (int i = t; i < n; i += nthreads) {
         float v = 0.f;
         for (int qq = 0; qq < nslices; ++qq) v += red[(size_t)qq * n + i];
         Hb[i] = v;
@@ -1788,7 +1796,10 @@ __global__ void __launch_bounds__(O2_WARPS * 32) obs_kernel3(const __grid_consta
 // The eval kernel streams BOTH operands through double-buffered shared-memory tiles
 // (cp.async), so it needs ~110 KB per CTA and is insensitive to HBM latency.
 // =========================================================================================
-template <bool SECOND>
+// CN1 / CKT > 0: layer width and tile length fixed at compile time (config 4: 64 / 112), which
+// turns a quarter of the kernel's instructions (address arithmetic on runtime strides) into
+// immediates; 0 = read them from the Dev.
+template <bool SECOND, int CN1 = 0, int CKT = 0>
 __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ Dev d,
                                                       const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -1796,7 +1807,8 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
     float *const X0 = sm + d.ev_X0, *const X1 = sm + d.ev_X1;
     float *const W0 = sm + d.ev_W0, *const W1 = sm + d.ev_W1;
     float *misc = sm + d.off_misc;
-    const int XS = d.ev_XS;
+    const int cN1 = CN1 ? CN1 : d.N1, cN1p = CN1 ? CN1 : d.N1p, cKT = CKT ? CKT : d.KT;
+    const int XS = CKT ? (((CKT >> 2) & 1) ? CKT : CKT + 4) : d.ev_XS;
     const int e_end = a.e_begin + a.e_count;
     for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
         EnvScalars *sc = d.sc + e;
@@ -1823,8 +1835,8 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
         __syncthreads();
 
         auto issue_x = [&](int t) {
-            const int k0 = t * d.KT;
-            const int kq = (min(d.KT, d.Dp - k0)) >> 2;          // 16-byte chunks per row
+            const int k0 = t * cKT;
+            const int kq = (min(cKT, d.Dp - k0)) >> 2;          // 16-byte chunks per row
             float *dst = (t & 1) ? X1 : X0;
             for (int i = tid; i < cnt * kq; i += blockDim.x) {
                 const int r = i / kq, c = i - r * kq;
@@ -1832,9 +1844,9 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
             }
         };
         auto issue_w = [&](int t) {
-            const int k0 = t * d.KT;
-            const int nq = (min(d.KT, d.D - k0) * d.N1) >> 2;
-            const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * d.N1);
+            const int k0 = t * cKT;
+            const int nq = (min(cKT, d.D - k0) * cN1) >> 2;
+            const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * cN1);
             float4 *dst = reinterpret_cast<float4 *>((t & 1) ? W1 : W0);
             for (int i = tid; i < nq; i += blockDim.x) cp_async16(dst + i, src + i);
         };
@@ -1847,16 +1859,16 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
             for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
         issue_x(0); issue_w(0); cp_async_commit();
         for (int t = 0; t < d.ntiles; ++t) {
-            const int krows = min(d.KT, d.D - t * d.KT), krows4 = (krows + 3) & ~3;
+            const int krows = min(cKT, d.D - t * cKT), krows4 = (krows + 3) & ~3;
             if (t + 1 < d.ntiles) { issue_x(t + 1); issue_w(t + 1); cp_async_commit(); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             float *T = (t & 1) ? W1 : W0;
-            for (int i = krows * d.N1p + tid; i < krows4 * d.N1p; i += blockDim.x) T[i] = 0.f;
+            for (int i = krows * cN1p + tid; i < krows4 * cN1p; i += blockDim.x) T[i] = 0.f;
             __syncthreads();
-            f_accumulate_fast(d, (t & 1) ? X1 : X0, XS, T, krows4, acc);
+            f_accumulate_fast<CN1>(d, (t & 1) ? X1 : X0, XS, T, krows4, acc);
             __syncthreads();
         }
-        f_store_fast(d, sm, acc);                            // partials reduced through the W tiles
+        f_store_fast<CN1>(d, sm, acc);                       // partials reduced through the W tiles
         // the first X tile of the backward pass can already travel
         issue_x(0); cp_async_commit();
         const float loss = tail_eval(d, sm, cnt);
@@ -1868,15 +1880,16 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
             gout[d.P1 + i] = g;
             gsum += g;
         }
-        const int rgi = tid / d.cg, cgi = tid - rgi * d.cg, kl = rgi * 4;
-        const int half = d.N1 >> 1;
+        const int ccg = cN1 >> 3;
+        const int rgi = tid / ccg, cgi = tid - rgi * ccg, kl = rgi * 4;
+        const int half = cN1 >> 1;
         const float *dp = sm + d.off_dP + 4 * cgi;
         for (int t = 0; t < d.ntiles; ++t) {
-            const int k0 = t * d.KT;
+            const int k0 = t * cKT;
             if (t + 1 < d.ntiles) { issue_x(t + 1); cp_async_commit(); cp_async_wait<1>(); }
             else cp_async_wait<0>();
             __syncthreads();
-            if (kl < d.KT && k0 + kl < d.D) {
+            if (kl < cKT && k0 + kl < d.D) {
                 const float *xr = ((t & 1) ? X1 : X0) + kl;
                 float g[4][8];
 #pragma unroll
@@ -1885,8 +1898,8 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
                     for (int c = 0; c < 8; ++c) g[j][c] = 0.f;
                 for (int s = 0; s < cnt; ++s) {
                     const float4 x = *reinterpret_cast<const float4 *>(xr + s * XS);
-                    const float4 d0 = *reinterpret_cast<const float4 *>(dp + s * d.N1p);
-                    const float4 d1 = *reinterpret_cast<const float4 *>(dp + s * d.N1p + half);
+                    const float4 d0 = *reinterpret_cast<const float4 *>(dp + s * cN1p);
+                    const float4 d1 = *reinterpret_cast<const float4 *>(dp + s * cN1p + half);
                     const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -1903,7 +1916,7 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (k0 + kl + j < d.D) {
-                        float *dst = gout + (size_t)(k0 + kl + j) * d.N1 + 4 * cgi;
+                        float *dst = gout + (size_t)(k0 + kl + j) * cN1 + 4 * cgi;
                         *reinterpret_cast<float4 *>(dst) = make_float4(g[j][0], g[j][1], g[j][2], g[j][3]);
                         *reinterpret_cast<float4 *>(dst + half) = make_float4(g[j][4], g[j][5], g[j][6], g[j][7]);
                         gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
@@ -2260,30 +2273,35 @@ __global__ void __launch_bounds__(256, 2) tc_eval_kernel(const __grid_constant__
 
 // ------------------------------------------------ thin eval kernel: no hidden layer
 // Softmax regression (BASELINE config 3: 784 -> 10): logits Z = X.W + b with at most 16
-// classes.  There is almost no arithmetic (1 MFLOP per env), the kernel is the minibatch
-// gather: X rows travel with 16-byte cp.async into shared memory once and serve the forward
-// and the backward pass; W sits beside it padded to 4-float groups.
-//   forward : warp = 4 samples at a time, lanes stride over k, W row read as float4s
-//   backward: thread = one feature k, all classes, all samples; gradient staged in shared
-//             memory and written with coalesced 16-byte stores
+// classes.  There is almost no arithmetic (1 MFLOP per env); the kernel is the minibatch
+// gather, so the feature axis is cut into chunks of KC <= 128 features that stream through
+// two small shared-memory buffers with 16-byte cp.async (X rows and the contiguous W chunk):
+// ~50 KB per CTA, four CTAs per SM hide each other's latencies.
+//   forward : warp = 4 samples, lanes stride over the chunk's features, logits accumulate in
+//             registers across the chunks, one shuffle reduction at the end
+//   backward: second pass over the chunks (L2 hits); thread = (feature, half of the samples);
+//             the chunk's gradient rows are contiguous in HBM and leave as 16-byte stores
 constexpr int THIN_CMAX = 16;
+constexpr int THIN_KC = 128;
+constexpr int THIN_STAGES = 4;                     // chunks in flight: the kernel is bound by load latency
 
 template <bool SECOND>
 __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ Dev d,
-                                                           const __grid_constant__ StepArgs a) {
+                                                        const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float misc[8];
     __shared__ double red[NSTAT * 8];
+    __shared__ int idx_s[64], ys[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = d.D, C = d.C, B = d.B, XS = d.Ds;
-    const int Cq = (C + 3) & ~3;
-    float *Xs = sm;                                   // [B][XS]
-    float *Ws = Xs + B * XS;                          // [D][Cq], later the gradient [D][C]
-    float *bs = Ws + D * Cq;                          // [Cq]
-    float *Zs = bs + THIN_CMAX;                       // [B][Cq] logits, then dZ
-    float *lb = Zs + B * THIN_CMAX;                   // [B]
-    int *idx_s = reinterpret_cast<int *>(lb + B);     // [B]
-    int *ys = idx_s + B;                              // [B]
+    const int D = d.D, C = d.C, B = d.B, KC = d.KT;               // KT = chunk length here
+    const int XS = KC + 4;                                        // row stride of an X chunk (16-byte rows)
+    const int nch = (D + KC - 1) / KC;
+    float *Xb0 = sm;                                              // [THIN_STAGES][B][XS]
+    float *Wb0 = Xb0 + THIN_STAGES * B * XS;                      // [THIN_STAGES][KC][C]
+    float *Gs = Wb0 + THIN_STAGES * KC * C;                       // [2][KC][C] partial gradients of the chunk
+    float *Zs = Gs + 2 * KC * C;                                  // [B][16] logits, then dZ
+    float *lb = Zs + B * THIN_CMAX;                               // [B]
+    float *bs = lb + B;                                           // [16]
     const int e_end = a.e_begin + a.e_count;
     for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
         EnvScalars *sc = d.sc + e;
@@ -2293,62 +2311,75 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
         current_batch(d, a, e, sc, idx, cnt);
         __syncthreads();
         for (int r = tid; r < B; r += blockDim.x) {
-            const int row = (r < cnt) ? idx[r] : 0;
+            const int row = (r < cnt) ? idx[r] : -1;
             idx_s[r] = row;
-            ys[r] = (r < cnt) ? d.labels[row] : 0;
-        }
-        __syncthreads();
-        const int kq = d.Dp >> 2;
-        for (int i = tid; i < cnt * kq; i += blockDim.x) {
-            const int r = i / kq, c = i - r * kq;
-            cp_async16(Xs + r * XS + 4 * c, d.X + (size_t)idx_s[r] * d.Dp + 4 * c);
-        }
-        cp_async_commit();
-        for (int i = tid; i < D * Cq; i += blockDim.x) {
-            const int k = i / Cq, c = i - k * Cq;
-            Ws[i] = c < C ? wE[k * C + c] : 0.f;
+            ys[r] = row >= 0 ? d.labels[row] : 0;
         }
         if (tid < THIN_CMAX) bs[tid] = tid < C ? wE[d.P1 + tid] : 0.f;
-        cp_async_wait<0>();
         __syncthreads();
-        // ---- forward: 4 samples per warp pass
-        for (int s0 = warp * 4; s0 < B; s0 += 32) {
-            float acc[4][THIN_CMAX];
+        auto issue = [&](int ch, bool with_w) {
+            const int k0 = ch * KC, krows = min(KC, D - k0), kq = (krows + 3) >> 2;
+            float *xb = Xb0 + (ch % THIN_STAGES) * B * XS;
+            for (int r = warp; r < B; r += 8) {                   // warp = row, lanes = its 16-byte pieces
+                const int row = idx_s[r];
+                for (int c = lane; c < kq; c += 32) {
+                    if (row >= 0) cp_async16(xb + r * XS + 4 * c, d.X + (size_t)row * d.Dp + k0 + 4 * c);
+                    else *reinterpret_cast<float4 *>(xb + r * XS + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (with_w) {
+                float *wb = Wb0 + (ch % THIN_STAGES) * KC * C;
+                const float *src = wE + (size_t)k0 * C;
+                const int n = krows * C, nq = n >> 2;             // k0 * C is a multiple of 4 (KC * C % 4 == 0)
+                for (int i = tid; i < nq; i += blockDim.x) cp_async16(wb + 4 * i, src + 4 * i);
+                for (int i = 4 * nq + tid; i < n; i += blockDim.x) wb[i] = src[i];
+            }
+            cp_async_commit();
+        };
+        // ---- forward: Z[s][c] accumulated over the chunks, warp = 4 samples per pass
+        float acc[4][THIN_CMAX];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < THIN_CMAX; ++c) acc[i][c] = 0.f;
-            const float *x0 = Xs + min(s0, B - 1) * XS, *x1 = Xs + min(s0 + 1, B - 1) * XS;
-            const float *x2 = Xs + min(s0 + 2, B - 1) * XS, *x3 = Xs + min(s0 + 3, B - 1) * XS;
-            for (int k = lane; k < D; k += 32) {
-                const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
-                const float4 *wr = reinterpret_cast<const float4 *>(Ws + k * Cq);
+            for (int c = 0; c < THIN_CMAX; ++c) acc[i][c] = 0.f;
+        const int s0 = warp * 4;                                  // B <= 32: one pass of 8 warps x 4 samples
+        for (int ch = 0; ch < THIN_STAGES - 1; ++ch) { if (ch < nch) issue(ch, true); else cp_async_commit(); }
+        for (int ch = 0; ch < nch; ++ch) {
+            if (ch + THIN_STAGES - 1 < nch) issue(ch + THIN_STAGES - 1, true); else cp_async_commit();
+            cp_async_wait<THIN_STAGES - 1>();                     // chunk ch has landed
+            __syncthreads();
+            const int krows = min(KC, D - ch * KC);
+            const float *xb = Xb0 + (ch % THIN_STAGES) * B * XS, *wb = Wb0 + (ch % THIN_STAGES) * KC * C;
+            if (s0 < B) {
+                const float *x0 = xb + min(s0, B - 1) * XS, *x1 = xb + min(s0 + 1, B - 1) * XS;
+                const float *x2 = xb + min(s0 + 2, B - 1) * XS, *x3 = xb + min(s0 + 3, B - 1) * XS;
+                for (int k = lane; k < krows; k += 32) {
+                    const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
+                    const float *wr = wb + k * C;
 #pragma unroll
-                for (int q = 0; q < THIN_CMAX / 4; ++q) {
-                    if (4 * q < Cq) {
-                        const float4 w4 = wr[q];
+                    for (int c = 0; c < THIN_CMAX; ++c) {
+                        if (c < C) {
+                            const float w = wr[c];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            acc[i][4 * q] = fmaf(xv[i], w4.x, acc[i][4 * q]);
-                            acc[i][4 * q + 1] = fmaf(xv[i], w4.y, acc[i][4 * q + 1]);
-                            acc[i][4 * q + 2] = fmaf(xv[i], w4.z, acc[i][4 * q + 2]);
-                            acc[i][4 * q + 3] = fmaf(xv[i], w4.w, acc[i][4 * q + 3]);
+                            for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(xv[i], w, acc[i][c]);
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int c = 0; c < THIN_CMAX; ++c) {
-                    if (c < Cq) {
-                        float v = acc[i][c];
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        if (lane == 0 && s0 + i < B) Zs[(s0 + i) * THIN_CMAX + c] = v + bs[c];
-                    }
-                }
+            __syncthreads();
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < THIN_CMAX; ++c) {
+                if (c < C) {
+                    float v = acc[i][c];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && s0 + i < B) Zs[(s0 + i) * THIN_CMAX + c] = v + bs[c];
+                }
+            }
         __syncthreads();
+        for (int ch = 0; ch < THIN_STAGES - 1; ++ch) { if (ch < nch) issue(ch, false); else cp_async_commit(); }   // backward pass travels
         // ---- softmax cross-entropy per sample, dZ in place (problems/optimize_nn.py:47-50)
         for (int s = tid; s < B; s += blockDim.x) {
             float *z = Zs + s * THIN_CMAX;
@@ -2369,38 +2400,62 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
             lb[s] = loss;
         }
         __syncthreads();
-        float loss = 0.f;
-        for (int s = 0; s < cnt; ++s) loss += lb[s];
-        loss /= (float)cnt;
-        // ---- backward: thread = feature k; gradient staged over W (no longer needed)
-        float gsum = 0.f;
-        for (int k = tid; k < D; k += blockDim.x) {
-            float g[THIN_CMAX];
-#pragma unroll
-            for (int c = 0; c < THIN_CMAX; ++c) g[c] = 0.f;
-            for (int s = 0; s < cnt; ++s) {
-                const float x = Xs[s * XS + k];
-                const float4 *dz = reinterpret_cast<const float4 *>(Zs + s * THIN_CMAX);
-#pragma unroll
-                for (int q = 0; q < THIN_CMAX / 4; ++q) {
-                    if (4 * q < Cq) {
-                        const float4 d4 = dz[q];
-                        g[4 * q] = fmaf(x, d4.x, g[4 * q]);
-                        g[4 * q + 1] = fmaf(x, d4.y, g[4 * q + 1]);
-                        g[4 * q + 2] = fmaf(x, d4.z, g[4 * q + 2]);
-                        g[4 * q + 3] = fmaf(x, d4.w, g[4 * q + 3]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < THIN_CMAX; ++c)
-                if (c < C) { Ws[k * C + c] = g[c]; gsum += g[c]; }
+        if (warp == 0) {                                          // mean loss, summed in sample order by one lane
+            float l = 0.f;
+            if (lane == 0) { for (int s = 0; s < cnt; ++s) l += lb[s]; misc[0] = l / (float)cnt; }
         }
         __syncthreads();
-        for (int i = tid * 4; i < d.P1; i += blockDim.x * 4) {
-            if (i + 3 < d.P1) *reinterpret_cast<float4 *>(gout + i) = *reinterpret_cast<const float4 *>(Ws + i);
-            else for (int j = i; j < d.P1; ++j) gout[j] = Ws[j];
+        const float loss = misc[0];
+        // ---- backward: thread = (feature k of the chunk, half h of the samples)
+        float gsum = 0.f;
+        const int kk = tid & (THIN_KC - 1), hh = tid >> 7;
+        const int s_lo = hh * ((B + 1) >> 1), s_hi = hh ? B : ((B + 1) >> 1);
+        for (int ch = 0; ch < nch; ++ch) {
+            if (ch + THIN_STAGES - 1 < nch) issue(ch + THIN_STAGES - 1, false); else cp_async_commit();
+            cp_async_wait<THIN_STAGES - 1>();
+            __syncthreads();
+            const int k0 = ch * KC, krows = min(KC, D - k0);
+            const float *xb = Xb0 + (ch % THIN_STAGES) * B * XS;
+            if (kk < krows) {
+                float g[THIN_CMAX];
+#pragma unroll
+                for (int c = 0; c < THIN_CMAX; ++c) g[c] = 0.f;
+                for (int s = s_lo; s < s_hi; ++s) {
+                    const float x = xb[s * XS + kk];
+                    const float4 *dz = reinterpret_cast<const float4 *>(Zs + s * THIN_CMAX);
+#pragma unroll
+                    for (int q = 0; q < THIN_CMAX / 4; ++q) {
+                        if (4 * q < C) {
+                            const float4 d4 = dz[q];
+                            g[4 * q] = fmaf(x, d4.x, g[4 * q]);
+                            g[4 * q + 1] = fmaf(x, d4.y, g[4 * q + 1]);
+                            g[4 * q + 2] = fmaf(x, d4.z, g[4 * q + 2]);
+                            g[4 * q + 3] = fmaf(x, d4.w, g[4 * q + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < THIN_CMAX; ++c)
+                    if (c < C) Gs[(hh * KC + kk) * C + c] = g[c];
+            }
+            __syncthreads();
+            // the chunk's gradient rows [k0, k0 + krows) x C are contiguous in HBM
+            const int n = krows * C;
+            float *dst = gout + (size_t)k0 * C;
+            for (int i = tid * 4; i < n; i += blockDim.x * 4) {
+                if (i + 3 < n) {
+                    const float4 u = *reinterpret_cast<const float4 *>(Gs + i);
+                    const float4 v = *reinterpret_cast<const float4 *>(Gs + KC * C + i);
+                    const float4 g4 = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+                    *reinterpret_cast<float4 *>(dst + i) = g4;
+                    gsum += (g4.x + g4.y) + (g4.z + g4.w);
+                } else {
+                    for (int j = i; j < n; ++j) { const float g = Gs[j] + Gs[KC * C + j]; dst[j] = g; gsum += g; }
+                }
+            }
+            // no barrier needed here: the next iteration's barrier orders these reads of Gs before its writes
         }
+        __syncthreads();
         if (tid < C) {
             float g = 0.f;
             for (int s = 0; s < cnt; ++s) g += Zs[s * THIN_CMAX + tid];
@@ -3057,8 +3112,10 @@ struct b2e_env {
     size_t smem_obs;
     int chunk_envs, obs_grid;
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
+    bool eval_c;                     // eval_kernel instantiated for N1 = 64, KT = 112 (config 4)
     bool use_thin;                   // softmax regression: thin_eval_kernel
     size_t smem_thin;
+    int thin_kc;
     bool use_tc;                     // tcgen05 eval kernel replaces eval_kernel
     Dev d_tc;                        // Dev with the tensor-core kernel's shared-memory layout
     size_t smem_tc;
@@ -3244,9 +3301,14 @@ int configure(b2e_handle h) {
     // large problems run as a pipeline of kernels (eval / update / eval / observations)
     h->use_eval_kernel = d.fast && d.nks * d.B * d.N1p <= 2 * round_up(d.KT, 4) * d.N1p;
     if (d.generic) { h->use_eval_kernel = false; d.fast = 0; }
-    h->smem_thin = (size_t)(d.B * d.Ds + d.D * ((d.C + 3) & ~3) + THIN_CMAX + d.B * THIN_CMAX + 3 * d.B + 8) * sizeof(float);
+    int thin_kc = 0;                                           // largest chunk <= 128 with KC*C % 4 == 0, dividing D if possible
+    for (int k = THIN_KC; k >= 8 && !thin_kc; k -= 4)
+        if ((k * d.C) % 4 == 0 && d.D % k == 0) thin_kc = k;
+    if (!thin_kc) thin_kc = (d.C % 4 == 0) ? THIN_KC : ((d.C % 2 == 0) ? THIN_KC : THIN_KC);
+    h->smem_thin = (size_t)(THIN_STAGES * d.B * (thin_kc + 4) + (THIN_STAGES + 2) * thin_kc * d.C + d.B * THIN_CMAX + d.B + THIN_CMAX + 8) * sizeof(float);
     h->use_thin = !d.generic && !h->use_eval_kernel && d.kind == B2E_PROBLEM_SOFTMAX && !d.hidden &&
-                  d.C <= THIN_CMAX && d.P >= 4096 && h->smem_thin <= 200 * 1024;
+                  d.C <= THIN_CMAX && d.B <= 32 && d.P >= 4096 && (thin_kc * d.C) % 4 == 0 && d.D % 4 == 0;
+    h->thin_kc = thin_kc;
     d.split = (c.env_kind == B2E_ENV_MULTIOPTIMIZE || h->use_eval_kernel || h->use_thin || d.generic) ? 1 : 0;
     // shared memory carve-up (float offsets, all multiples of 4)
     d.xslack = round_up(d.KR + 8, 4) > 64 ? round_up(d.KR + 8, 4) : 64;
@@ -3545,8 +3607,13 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess ||
             cudaFuncSetAttribute(eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_eval) != cudaSuccess ||
+            cudaFuncSetAttribute(eval_kernel<false, 64, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_eval) != cudaSuccess ||
+            cudaFuncSetAttribute(eval_kernel<true, 64, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess)
             return bail("b2e_create: eval kernel does not fit shared memory");
+        h->eval_c = d.N1 == 64 && d.N1p == 64 && d.KT == 112 && d.B == 32 && !getenv("B2E_EVAL_GENERIC");
         int occ_ev = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, eval_kernel<true>, 256, h->smem_eval) !=
                 cudaSuccess || occ_ev < 1)
@@ -3699,12 +3766,13 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             const int cap = h->use_tc ? h->tc_grid : h->eval_grid;
             const int grid_ev = d.E < cap ? d.E : cap;
             if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
+            else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
         } else if (h->use_thin) {
             const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
-            thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
+            { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
         } else {
@@ -3738,9 +3806,10 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
-        eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
+        { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {                                                 // generic dense stack
         StepArgs b = a;
         b.mode = MODE_EVAL_FIRST;
@@ -3753,9 +3822,10 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
-        eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(d, a);
+        { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {
         StepArgs b = a;
         b.mode = MODE_EVAL_STEP;
