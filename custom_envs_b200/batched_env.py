@@ -198,19 +198,23 @@ class BatchedOptEnv:
                                        _ptr(self.obs), self._stream()))
         return self.obs
 
-    def step(self, actions, batch_idx=None, batch_cnt=None):
+    def step(self, actions, batch_idx=None, batch_cnt=None, obs_out=None):
         """actions: [E*P] (or [E*P,1]) float32 device tensor in VecEnv row order.
         -> (obs [E*P,obs_dim], reward [E] f32, done [E] u8, info [E,16] f64): views of
-        buffers that the next step overwrites."""
+        buffers that the next step overwrites.  ``obs_out``: write the observation rows there
+        instead (any device-accessible float32 buffer of that shape, e.g. pinned host memory:
+        the rows then cross PCIe straight from the observation kernel)."""
         actions = actions.reshape(-1)
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, torch.float32).contiguous()
         assert actions.numel() == self.num_rows
         idx, cnt = self._idx(batch_idx, batch_cnt)
-        self._check(self.lib.b2e_step(self.handle, _ptr(actions), _ptr(idx), _ptr(cnt), _ptr(self.obs),
+        obs = self.obs if obs_out is None else obs_out
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.obs.numel()
+        self._check(self.lib.b2e_step(self.handle, _ptr(actions), _ptr(idx), _ptr(cnt), _ptr(obs),
                                       _ptr(self.reward), _ptr(self.done), _ptr(self.info),
                                       self._stream()))
-        return self.obs, self.reward, self.done, self.info
+        return obs, self.reward, self.done, self.info
 
     def evaluate(self, batch_idx=None, batch_cnt=None):
         """BaseProblem.get for every env: (grad [E,P], loss [E]) on the current minibatch."""

@@ -564,11 +564,13 @@ __device__ void forward_from_global_fast(const Dev &d, float *sm, const float *w
 // ---------------------------------------------------------------------- the tail
 // Everything after the first matmul: bias/relu/second layer/softmax-CE (or MSE, or the
 // Rosenbrock function).  Fills dPre [B,N1p] and the tail gradient tg; returns mean loss.
+// CN1 / CC > 0 fix the hidden width / class count (and B = 32) at compile time.
+template <int CN1 = 0, int CC = 0>
 __device__ float tail_eval(const Dev &d, float *sm, int cnt) {
     float *Hb = sm + d.off_H, *dP = sm + d.off_dP, *tw = sm + d.off_tw, *tg = sm + d.off_tg;
     float *Zb = sm + d.off_Z, *lb = sm + d.off_lb, *misc = sm + d.off_misc;
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (d.kind == B2E_PROBLEM_FUNC) {                 // utils/utils_functions.py:4-6
+    if (!CN1 && d.kind == B2E_PROBLEM_FUNC) {         // utils/utils_functions.py:4-6
         if (tid == 0) {
             const float x = tw[0], y = tw[1], t = y - x * x;
             misc[0] = 100.f * t * t + (1.f - x) * (1.f - x);
@@ -578,12 +580,14 @@ __device__ float tail_eval(const Dev &d, float *sm, int cnt) {
         __syncthreads();
         return misc[0];
     }
-    const int N1 = d.N1, N1p = d.N1p, C = d.C;
+    const int N1 = CN1 ? CN1 : d.N1, N1p = CN1 ? CN1 : d.N1p, C = CC ? CC : d.C;
+    const int nB = CN1 ? 32 : d.B;
+    const bool hidden = CN1 ? true : (d.hidden != 0);
     const float *b1 = tw, *W2 = tw + N1, *b2 = tw + N1 + N1 * C;
-    float *Z = d.hidden ? Zb : Hb;
-    const int Zs = d.hidden ? d.Cp : N1p;
-    float *dZ = d.hidden ? Zb : dP;                   // dZ overwrites Z when hidden
-    if (d.hidden) {
+    float *Z = hidden ? Zb : Hb;
+    const int Zs = hidden ? (CC ? ((CC + 3) & ~3) : d.Cp) : N1p;
+    float *dZ = hidden ? Zb : dP;                     // dZ overwrites Z when hidden
+    if (hidden) {
         for (int i = tid; i < cnt * N1; i += nt) {
             const int s = i / N1, j = i - s * N1;
             const float v = Hb[s * N1p + j] + b1[j];
@@ -603,7 +607,7 @@ __device__ float tail_eval(const Dev &d, float *sm, int cnt) {
         }
     }
     __syncthreads();
-    for (int s = tid; s < d.B; s += nt) {
+    for (int s = tid; s < nB; s += nt) {
         float loss = 0.f;
         if (s < cnt) {
             const float *z = Z + s * Zs;
@@ -640,7 +644,7 @@ __device__ float tail_eval(const Dev &d, float *sm, int cnt) {
         for (int s = 0; s < cnt; ++s) l += lb[s];
         misc[0] = l / (float)cnt;
     }
-    if (d.hidden) {
+    if (hidden) {
         float *gb1 = tg, *gW2 = tg + N1, *gb2 = tg + N1 + N1 * C;
         for (int i = tid; i < N1 * C; i += nt) {
             const int j = i / C, c = i - j * C;
@@ -653,7 +657,7 @@ __device__ float tail_eval(const Dev &d, float *sm, int cnt) {
             for (int s = 0; s < cnt; ++s) g += dZ[s * Zs + c];
             gb2[c] = g;
         }
-        for (int i = tid; i < d.B * N1; i += nt) {
+        for (int i = tid; i < nB * N1; i += nt) {
             const int s = i / N1, j = i - s * N1;
             float v = 0.f;
             if (s < cnt && Hb[s * N1p + j] > 0.f) {
@@ -1871,7 +1875,7 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
         f_store_fast<CN1>(d, sm, acc);                       // partials reduced through the W tiles
         // the first X tile of the backward pass can already travel
         issue_x(0); cp_async_commit();
-        const float loss = tail_eval(d, sm, cnt);
+        const float loss = (CN1 == 64 && d.C == 10) ? tail_eval<CN1, 10>(d, sm, cnt) : tail_eval(d, sm, cnt);
 
         // ---- backward: tail gradient, then g = X^T . dPre tile by tile, straight to HBM
         float gsum = 0.f;
@@ -2182,7 +2186,7 @@ __global__ void __launch_bounds__(256, 2) tc_eval_kernel(const __grid_constant__
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // ================= tail: bias, relu, second layer, softmax-CE -> dPre [B][N1], tail gradient
-        const float loss = tail_eval(d, sm, cnt);
+        const float loss = d.C == 10 ? tail_eval<64, 10>(d, sm, cnt) : tail_eval(d, sm, cnt);
         float gsum = 0.f;
         for (int i = tid; i < d.tailP; i += blockDim.x) {
             const float g = sm[d.off_tg + i];
