@@ -1840,7 +1840,8 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
 
         auto issue_x = [&](int t) {
             const int k0 = t * cKT;
-            const int kq = (min(cKT, d.Dp - k0)) >> 2;          // 16-byte chunks per row
+            // 16-byte chunks per row; the fixed-shape instantiation is only used when CKT divides D
+            const int kq = CKT ? CKT / 4 : (min(cKT, d.Dp - k0)) >> 2;
             float *dst = (t & 1) ? X1 : X0;
             for (int i = tid; i < cnt * kq; i += blockDim.x) {
                 const int r = i / kq, c = i - r * kq;
@@ -1849,7 +1850,7 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
         };
         auto issue_w = [&](int t) {
             const int k0 = t * cKT;
-            const int nq = (min(cKT, d.D - k0) * cN1) >> 2;
+            const int nq = (CKT && CN1) ? CKT * CN1 / 4 : (min(cKT, d.D - k0) * cN1) >> 2;
             const float4 *src = reinterpret_cast<const float4 *>(wE + (size_t)k0 * cN1);
             float4 *dst = reinterpret_cast<float4 *>((t & 1) ? W1 : W0);
             for (int i = tid; i < nq; i += blockDim.x) cp_async16(dst + i, src + i);
@@ -3617,7 +3618,8 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             cudaFuncSetAttribute(eval_kernel<true, 64, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess)
             return bail("b2e_create: eval kernel does not fit shared memory");
-        h->eval_c = d.N1 == 64 && d.N1p == 64 && d.KT == 112 && d.B == 32 && !getenv("B2E_EVAL_GENERIC");
+        h->eval_c = d.N1 == 64 && d.N1p == 64 && d.KT == 112 && d.B == 32 && d.D % 112 == 0 && d.Dp == d.D &&
+                    !getenv("B2E_EVAL_GENERIC");
         int occ_ev = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, eval_kernel<true>, 256, h->smem_eval) !=
                 cudaSuccess || occ_ev < 1)

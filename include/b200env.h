@@ -83,8 +83,9 @@ typedef struct b2e_config {
     uint64_t init_seed;           /* seed of the on-device Glorot-uniform initialiser */
 } b2e_config;
 
-/* OptVecEnv.__init__ + MultiOptLRs.__init__ + get_problem (vectorize/optvecenv.py:60-68,
- * envs/multioptlrs.py:39-61, problems/__init__.py:7-16).  Allocates all device state. */
+/* OptVecEnv.__init__ + MultiOptLRs.__init__ / MultiOptimize.__init__ + get_problem
+ * (vectorize/optvecenv.py:60-68, envs/multioptlrs.py:39-61, envs/multioptimize.py:40-76,
+ * problems/__init__.py:7-16).  Allocates all device state. */
 int b2e_create(const b2e_config *cfg, b2e_handle *out);
 void b2e_destroy(b2e_handle h);
 /* Text of the last error on this handle (or of the last failed b2e_create if h is NULL). */
