@@ -3118,6 +3118,7 @@ struct b2e_env {
     int chunk_envs, obs_grid;
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
     bool eval_c;                     // eval_kernel instantiated for N1 = 64, KT = 112 (config 4)
+    int nchunks, eval_ctas_per_sm;   // B2E_CHUNKS experiment
     bool use_thin;                   // softmax regression: thin_eval_kernel
     size_t smem_thin;
     int thin_kc;
@@ -3506,6 +3507,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (!h) return fail(nullptr, "b2e_create: out of host memory");
     h->cfg = *cfg;
     h->launches = 0;
+    h->nchunks = 1; h->eval_ctas_per_sm = 2; h->eval_c = false;
     h->dataset_bound = h->stream_bound = false;
     h->trace = false; h->tr_count = 0;
     for (auto &ev : h->tr) ev = nullptr;
@@ -3620,11 +3622,23 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             return bail("b2e_create: eval kernel does not fit shared memory");
         h->eval_c = d.N1 == 64 && d.N1p == 64 && d.KT == 112 && d.B == 32 && d.D % 112 == 0 && d.Dp == d.D &&
                     !getenv("B2E_EVAL_GENERIC");
+        h->nchunks = getenv("B2E_CHUNKS") ? atoi(getenv("B2E_CHUNKS")) : 1;
+        if (h->nchunks > 1) {
+            int prio_least = 0, prio_greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+            if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+                cudaStreamCreateWithPriority(&h->hi, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_chunk[0], cudaEventDisableTiming) != cudaSuccess)
+                return bail("b2e_create: stream/event creation failed");
+        }
         int occ_ev = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, eval_kernel<true>, 256, h->smem_eval) !=
                 cudaSuccess || occ_ev < 1)
             return bail("b2e_create: eval kernel does not fit an SM");
         h->eval_grid = occ_ev * h->num_sms;
+        h->eval_ctas_per_sm = getenv("B2E_EVAL_CTAS") ? atoi(getenv("B2E_EVAL_CTAS")) : occ_ev;
         h->chunk_envs = 4 * h->num_sms;
         h->obs_grid = 1 << 30;
     }
@@ -3808,6 +3822,40 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     const int cap_ev = h->use_tc ? h->tc_grid : h->eval_grid;
     const int grid_ev = d.E < cap_ev ? d.E : cap_ev;
     auto mark = [&](int i) { if (h->trace) cudaEventRecord(h->tr[i], main_s); };
+    if (h->nchunks > 1 && h->eval_c && !h->use_tc && (h->obs_stages || h->obs_regs)) {
+        // experiment (B2E_CHUNKS=n): env chunks alternate between two internal streams so that the
+        // FFMA-bound eval kernels of one chunk can share the SMs with the HBM-bound update /
+        // observation kernels of the other
+        cudaStream_t st[2] = {h->side, h->hi};
+        CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_s));
+        CUDA_TRY(h, cudaStreamWaitEvent(st[0], h->ev_fork, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(st[1], h->ev_fork, 0));
+        const int chunk = (d.E + h->nchunks - 1) / h->nchunks;
+        const void *fn = obs2_fn(h->obs_stages, h->obs_regs, h->obs_bulk);
+        for (int c = 0; c < h->nchunks; ++c) {
+            StepArgs b = a;
+            b.e_begin = c * chunk;
+            b.e_count = d.E - b.e_begin < chunk ? d.E - b.e_begin : chunk;
+            if (b.e_count <= 0) break;
+            cudaStream_t s2 = st[c & 1];
+            const int cap = h->eval_ctas_per_sm * h->num_sms;
+            const int g = b.e_count < cap ? b.e_count : cap;
+            eval_kernel<false, 64, 112><<<g, 256, h->smem_eval, s2>>>(dv, b);
+            update_kernel<<<dim3(d.nsegU, b.e_count), 256, 0, s2>>>(d, b);
+            eval_kernel<true, 64, 112><<<g, 256, h->smem_eval, s2>>>(dv, b);
+            const int grid2 = (d.nseg * b.e_count + O2_WARPS - 1) / O2_WARPS;
+            void *params[2] = {(void *)&d, (void *)&b};
+            CUDA_TRY(h, cudaLaunchKernel(fn, dim3(grid2), dim3(O2_WARPS * 32), params, h->smem_obs2, s2));
+            h->launches += 4;
+        }
+        CUDA_TRY(h, cudaEventRecord(h->ev_join, st[0]));
+        CUDA_TRY(h, cudaStreamWaitEvent(main_s, h->ev_join, 0));
+        CUDA_TRY(h, cudaEventRecord(h->ev_chunk[0], st[1]));
+        CUDA_TRY(h, cudaStreamWaitEvent(main_s, h->ev_chunk[0], 0));
+        h->tr_count = 0;
+        CUDA_TRY(h, cudaGetLastError());
+        goto after_pipeline;
+    }
     mark(0);
     if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
@@ -3854,6 +3902,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     h->tr_count = h->trace ? 4 : 0;
     h->launches += 4;
     CUDA_TRY(h, cudaGetLastError());
+after_pipeline:
     info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
