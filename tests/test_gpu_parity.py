@@ -144,6 +144,18 @@ def test_step_parity_from_identical_states(name, row_order, monkeypatch):
     """Per-step parity with host-supplied minibatch indices (external index mode).
     ``-generic`` forces the shape-agnostic dense-stack pipeline onto shapes the fused kernels
     also cover, so both implementations are held to the same oracle."""
+    _step_parity(name, row_order, monkeypatch, 5)
+
+
+@pytest.mark.parametrize('depth', [1, 3, 8])
+@pytest.mark.parametrize('name', ['iris_softmax', 'mlp_784x64x10'])
+def test_step_parity_other_history_depths(name, depth, monkeypatch):
+    """max_history other than the default 5 (search_optimize_hyperparam.py draws 5..25): the
+    run-time-depth variants of the fused epilogue and of the observation kernel."""
+    _step_parity(name, 'lexicographic', monkeypatch, depth)
+
+
+def _step_parity(name, row_order, monkeypatch, depth):
     BatchedOptEnv, _ = _mods()
     spec, num_rows, batch, num_envs = SPECS[name]
     if row_order.endswith('-tc'):
@@ -160,7 +172,7 @@ def test_step_parity_from_identical_states(name, row_order, monkeypatch):
     func = spec.kind == 'func'
     feats, targs = (None, None) if func else make_data(spec, num_rows)
     rng = np.random.RandomState(2)
-    max_batches, depth = 7, 5
+    max_batches = 7
     env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch,
                         max_batches=max_batches, max_history=depth, row_order=row_order,
                         index_mode='external', auto_reset=False)
