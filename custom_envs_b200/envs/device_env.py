@@ -73,6 +73,25 @@ class DeviceEnvFront(BaseMultiEnvironment):
             self.model._bind(self._backend, 0)
         return self._backend
 
+    # inside a fused OptVecEnv the step counters of all envs live in one numpy array that the
+    # VecEnv updates once per step; the attribute of the reference (baseenvironment.py:13,37)
+    # reads through to it
+    _shared_steps = None
+
+    @property
+    def current_step(self):
+        if self._shared_steps is not None:
+            steps, slot = self._shared_steps
+            return int(steps[slot])
+        return self._current_step
+
+    @current_step.setter
+    def current_step(self, value):
+        self._current_step = value
+        if self._shared_steps is not None:
+            steps, slot = self._shared_steps
+            steps[slot] = value
+
     def _host_reset_done(self):
         self.current_step = 0
 

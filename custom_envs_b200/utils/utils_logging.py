@@ -46,18 +46,23 @@ class Monitor(Wrapper):
                       'episode': self.current_episode})
         self.rewards.append(reward)
         if done:
-            elapsed = time.time() - self.t_start
-            total = sum(self.rewards)
-            episode = {'r': round(total, 6), 'l': len(self.rewards), 't': round(elapsed, 6),
-                       'current_reward': reward, 'episode': self.current_episode}
-            self.last_info = info
-            episode.update({key: info[key] for key in self.info_keywords})
-            self._sink.add(episode)
-            info['episode'] = episode
-            self.metric_history['rewards'].append(total)
-            self.metric_history['lengths'].append(len(self.rewards))
-            self.metric_history['times'].append(elapsed)
+            self._finish_episode(sum(self.rewards), len(self.rewards), reward, info)
         return observation, reward, done, info
+
+    def _finish_episode(self, total, length, reward, info):
+        """The episode-end branch of ``step`` (reference utils_logging.py:104-113).  The fused
+        ``OptVecEnv`` calls it directly with the episode's reward sum and length, which it keeps
+        vectorised over the envs."""
+        elapsed = time.time() - self.t_start
+        episode = {'r': round(total, 6), 'l': length, 't': round(elapsed, 6),
+                   'current_reward': reward, 'episode': self.current_episode}
+        self.last_info = info
+        episode.update({key: info[key] for key in self.info_keywords})
+        self._sink.add(episode)
+        info['episode'] = episode
+        self.metric_history['rewards'].append(total)
+        self.metric_history['lengths'].append(length)
+        self.metric_history['times'].append(elapsed)
 
     def close(self):
         self._sink.flush()

@@ -280,6 +280,19 @@ class OptVecEnv(VecEnv):
             self._impl = DeviceOptVecEnv(backend, first.observation_space.spaces[names[0]],
                                          first.action_space.spaces[names[0]], copy_outputs=False)
             self._wrapped = [env is not core for env, core in zip(environments, cores)]
+            # Fast path for the scripts' usual chain, one callback-free Monitor around each env
+            # (search_optimize_hyperparam.py:97-110): per-step bookkeeping is vectorised over the
+            # envs and the per-env Python objects are only touched when an episode ends.
+            from custom_envs_b200.utils.utils_logging import Monitor as _LenientMonitor
+            self._fast_monitor = all(
+                (env is core) or (type(env) is _LenientMonitor and env.env is core and not env.callbacks)
+                for env, core in zip(environments, cores))
+            self._ep_sum = np.zeros(len(cores), np.float64)
+            self._ep_len = np.zeros(len(cores), np.int64)
+            self._steps = np.zeros(len(cores), np.int64)
+            if self._fast_monitor:
+                for slot, core in enumerate(cores):
+                    core._shared_steps = (self._steps, slot)
         else:
             self._impl = _GenericOptVecEnv(environments)
             self._wrapped = None
@@ -294,6 +307,9 @@ class OptVecEnv(VecEnv):
     def reset(self):
         states = self._impl.reset()
         if self.is_device_backed:
+            self._ep_sum[:] = 0.0
+            self._ep_len[:] = 0
+            self._steps[:] = 0
             for env, core in zip(self._chains, self._cores):
                 core._host_reset_done()
                 if env is not core:
@@ -318,7 +334,25 @@ class OptVecEnv(VecEnv):
             done_env = impl._done_host.numpy().astype(bool)
             info_array = impl._info_host.numpy().copy()
             overrides = {}
-            for e, (env, core) in enumerate(zip(self._chains, self._cores)):
+            if self._fast_monitor:
+                # sum(self.rewards) in Monitor.step adds the float rewards in step order: a
+                # running float64 sum per env is the same arithmetic
+                self._ep_sum += reward_env.astype(np.float64)
+                self._ep_len += 1
+                self._steps[:] = info_array[:, 15].astype(np.int64)
+                for e in np.nonzero(done_env)[0]:
+                    env, core = self._chains[e], self._cores[e]
+                    self._steps[e] = 0
+                    if env is not core:
+                        info = info_row_to_dict(info_array[e])
+                        env._finish_episode(float(self._ep_sum[e]), int(self._ep_len[e]),
+                                            float(reward_env[e]), info)
+                        overrides[e] = info
+                        env.rewards = []                       # what Monitor.reset does
+                        env.current_episode += 1
+                    self._ep_sum[e] = 0.0
+                    self._ep_len[e] = 0
+            for e, (env, core) in enumerate(() if self._fast_monitor else zip(self._chains, self._cores)):
                 core._host_step_done(info_array[e], bool(done_env[e]))
                 if env is core:
                     continue

@@ -131,6 +131,51 @@ def test_optvecenv_fuses_monitored_envs():
         assert len(frame) == 2 and set(keys) <= set(frame.columns) and list(frame['l']) == [5, 5]
 
 
+def test_vectorised_monitor_path_equals_per_env_replay():
+    """A callback-free Monitor around every env takes the vectorised bookkeeping path of the fused
+    OptVecEnv; a Monitor with a callback forces the per-env replay.  Same seeds -> same outputs,
+    same episode rows in the .mon.csv files."""
+    from custom_envs.vectorize import OptVecEnv
+    from custom_envs.utils.utils_logging import Monitor
+    from custom_envs_b200.compat import make
+    from custom_envs import load_data
+    data = load_data('iris', 32)
+    keys = ('loss', 'actions_mean', 'weights_mean')
+
+    def build(i, tmp, slow):
+        env = make('MultiOptLRs-v0', problem='nn', max_batches=4,
+                   problem_kwargs=dict(layers=(5,), data_set=data))
+        env.seed(100 + i)
+        return Monitor(env, os.path.join(tmp, 'env%d' % i), info_keywords=keys,
+                       callbacks=[lambda record: None] if slow else None)
+
+    runs = []
+    for slow in (False, True):
+        with tempfile.TemporaryDirectory() as tmp:
+            vec = OptVecEnv([partial(build, i, tmp, slow) for i in range(4)])
+            assert vec.is_device_backed and vec._fast_monitor == (not slow)
+            vec.reset()
+            outputs = []
+            for t in range(10):
+                actions = np.random.RandomState(t).uniform(0, 2, size=(vec.num_envs, 1)).astype(np.float32)
+                states, rewards, terminals, infos = vec.step(actions)
+                outputs.append((states.copy(), rewards.copy(), terminals.copy(),
+                                [infos[e * vec.agent_no_list[0]]['episode'] for e in range(4)]))
+            steps = vec.get_attr('current_step')
+            totals = vec.env_method('get_episode_rewards')
+            vec.close()
+            frames = [pd.read_csv(os.path.join(tmp, 'env%d.mon.csv' % i)).drop(columns=['t']) for i in range(4)]
+            runs.append((outputs, steps, totals, frames))
+    fast, slow = runs
+    assert fast[1] == slow[1] == [2, 2, 2, 2] and fast[2] == slow[2]
+    for (s0, r0, t0, e0), (s1, r1, t1, e1) in zip(fast[0], slow[0]):
+        assert np.array_equal(s0, s1) and np.array_equal(r0, r1) and np.array_equal(t0, t1)
+        for a, b in zip(e0, e1):
+            assert {k: v for k, v in a.items() if k != 't'} == {k: v for k, v in b.items() if k != 't'}
+    for a, b in zip(fast[3], slow[3]):
+        assert len(a) == 2 and a.equals(b)
+
+
 def test_device_optvecenv_matches_vecenv_oracle():
     """Host-buffer VecEnv path (lexicographic rows, auto-reset, internal stream) vs the oracle."""
     from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
