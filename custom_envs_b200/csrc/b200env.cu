@@ -205,6 +205,18 @@ __device__ void block_reduce(const Stats &st, Totals &tot, double *red) {
     __syncthreads();
 }
 
+// deterministic block sum of one value (fixed order); result in every thread
+__device__ double block_sum(double v, double *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    return t;
+}
+
 // ---------------------------------------------------------------- minibatch gather
 __device__ void load_batch(const Dev &d, float *sm, const int *idx_g, int cnt) {
     float *Xs = sm;
@@ -1933,12 +1945,8 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
         if (!SECOND) continue;
 
         // ---- scalars of the step (thread 0): history bookkeeping, reward, done, info
-        Stats st;
-        zero_stats(st);
-        st.f[ST_G] = gsum;
-        Totals tot;
-        block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
-        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+        const double gtot = block_sum((double)gsum, reinterpret_cast<double *>(sm + d.off_red2));
+        if (tid == 0) step_scalars(d, a, sc, e, loss, gtot, misc);
         __syncthreads();
         const bool wrap = misc[4] != 0.f;
         __syncthreads();
@@ -2261,12 +2269,8 @@ __global__ void __launch_bounds__(256, 2) tc_eval_kernel(const __grid_constant__
         if (!SECOND) continue;
         // ---- scalars of the step (thread 0): history bookkeeping, reward, done, info
         __syncthreads();                                          // the reduction scratch shares stage 1
-        Stats st;
-        zero_stats(st);
-        st.f[ST_G] = gsum;
-        Totals tot;
-        block_reduce(st, tot, reinterpret_cast<double *>(sm + d.off_red2));
-        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+        const double gtot = block_sum((double)gsum, reinterpret_cast<double *>(sm + d.off_red2));
+        if (tid == 0) step_scalars(d, a, sc, e, loss, gtot, misc);
         __syncthreads();
         const bool wrap = misc[4] != 0.f;
         __syncthreads();
@@ -2468,12 +2472,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
             gsum += g;
         }
         if (!SECOND) continue;
-        Stats st;
-        zero_stats(st);
-        st.f[ST_G] = gsum;
-        Totals tot;
-        block_reduce(st, tot, red);
-        if (tid == 0) step_scalars(d, a, sc, e, loss, tot.v[ST_G], misc);
+        const double gtot = block_sum((double)gsum, red);
+        if (tid == 0) step_scalars(d, a, sc, e, loss, gtot, misc);
         __syncthreads();
         const bool wrap = misc[4] != 0.f;
         __syncthreads();
@@ -2769,20 +2769,36 @@ __device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-            for (int k0 = 0; k0 < K; k0 += GT_K) {
+            // the global loads of K step k0 + GT_K are in flight while step k0 is multiplied
+            float ra[4], rb[4];
+            auto fetch = [&](int k0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int i = tid + j * 256;
                     int mm, kk;
                     if (ak == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
                     const int m = m0 + mm, k = k0 + kk;
-                    smA[kk * GT_LD + mm] = (m < M && k < K) ? A[m * am + k * ak] : 0.f;
+                    ra[j] = (m < M && k < K) ? A[m * am + k * ak] : 0.f;
                     int nn, kb;
                     if (bn == 1) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
                     const int n = n0 + nn, k2 = k0 + kb;
-                    smB[kb * GT_LD + nn] = (n < N && k2 < K) ? Bm[k2 * bk + n * bn] : 0.f;
+                    rb[j] = (n < N && k2 < K) ? Bm[k2 * bk + n * bn] : 0.f;
+                }
+            };
+            fetch(0);
+            for (int k0 = 0; k0 < K; k0 += GT_K) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = tid + j * 256;
+                    int mm, kk;
+                    if (ak == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }
+                    smA[kk * GT_LD + mm] = ra[j];
+                    int nn, kb;
+                    if (bn == 1) { nn = i & 63; kb = i >> 6; } else { kb = i & 15; nn = i >> 4; }
+                    smB[kb * GT_LD + nn] = rb[j];
                 }
                 __syncthreads();
+                if (k0 + GT_K < K) fetch(k0 + GT_K);
 #pragma unroll
                 for (int kk = 0; kk < GT_K; ++kk) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(smA + kk * GT_LD + ty * 4);
@@ -2805,17 +2821,6 @@ __device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak
                 }
         }
     }
-}
-
-__device__ double block_sum(double v, double *red) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += red[w];
-    return t;
 }
 
 __global__ void __launch_bounds__(256) gen_eval_kernel(const __grid_constant__ Dev d,
