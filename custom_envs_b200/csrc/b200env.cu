@@ -2823,7 +2823,7 @@ __device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak
     }
 }
 
-__global__ void __launch_bounds__(256) gen_eval_kernel(const __grid_constant__ Dev d,
+__global__ void __launch_bounds__(256, 2) gen_eval_kernel(const __grid_constant__ Dev d,
                                                        const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float smA[GT_K * GT_LD];
     __shared__ __align__(16) float smB[GT_K * GT_LD];
