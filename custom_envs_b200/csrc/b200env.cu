@@ -2294,7 +2294,8 @@ constexpr int THIN_CMAX = 16;
 constexpr int THIN_KC = 128;
 constexpr int THIN_STAGES = 4;                     // chunks in flight: the kernel is bound by load latency
 
-template <bool SECOND>
+// CC > 0 fixes the class count at compile time (config 3: 10), 0 reads it from the Dev.
+template <bool SECOND, int CC = 0>
 __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ Dev d,
                                                         const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -2302,7 +2303,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
     __shared__ double red[NSTAT * 8];
     __shared__ int idx_s[64], ys[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = d.D, C = d.C, B = d.B, KC = d.KT;               // KT = chunk length here
+    const int D = d.D, C = CC ? CC : d.C, B = d.B, KC = d.KT;     // KT = chunk length here
+    constexpr int CU = CC ? CC : THIN_CMAX;                       // unrolled class loops
     const int XS = KC + 4;                                        // row stride of an X chunk (16-byte rows)
     const int nch = (D + KC - 1) / KC;
     float *Xb0 = sm;                                              // [THIN_STAGES][B][XS]
@@ -2366,8 +2368,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
                     const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
                     const float *wr = wb + k * C;
 #pragma unroll
-                    for (int c = 0; c < THIN_CMAX; ++c) {
-                        if (c < C) {
+                    for (int c = 0; c < CU; ++c) {
+                        if (CC || c < C) {
                             const float w = wr[c];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(xv[i], w, acc[i][c]);
@@ -2380,8 +2382,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int c = 0; c < THIN_CMAX; ++c) {
-                if (c < C) {
+            for (int c = 0; c < CU; ++c) {
+                if (CC || c < C) {
                     float v = acc[i][c];
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                     if (lane == 0 && s0 + i < B) Zs[(s0 + i) * THIN_CMAX + c] = v + bs[c];
@@ -2433,8 +2435,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
                     const float x = xb[s * XS + kk];
                     const float4 *dz = reinterpret_cast<const float4 *>(Zs + s * THIN_CMAX);
 #pragma unroll
-                    for (int q = 0; q < THIN_CMAX / 4; ++q) {
-                        if (4 * q < C) {
+                    for (int q = 0; q < (CU + 3) / 4; ++q) {
+                        if (CC || 4 * q < C) {
                             const float4 d4 = dz[q];
                             g[4 * q] = fmaf(x, d4.x, g[4 * q]);
                             g[4 * q + 1] = fmaf(x, d4.y, g[4 * q + 1]);
@@ -2444,8 +2446,8 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < THIN_CMAX; ++c)
-                    if (c < C) Gs[(hh * KC + kk) * C + c] = g[c];
+                for (int c = 0; c < CU; ++c)
+                    if (CC || c < C) Gs[(hh * KC + kk) * C + c] = g[c];
             }
             __syncthreads();
             // the chunk's gradient rows [k0, k0 + krows) x C are contiguous in HBM
@@ -3594,6 +3596,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (cudaFuncSetAttribute(thin_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_thin) != cudaSuccess ||
             cudaFuncSetAttribute(thin_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_thin) != cudaSuccess ||
+            cudaFuncSetAttribute(thin_eval_kernel<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)h->smem_thin) != cudaSuccess ||
+            cudaFuncSetAttribute(thin_eval_kernel<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_thin) != cudaSuccess)
             return bail("b2e_create: thin eval kernel does not fit shared memory");
         int occ_ev = 0;
@@ -3797,7 +3803,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             CUDA_TRY(h, cudaGetLastError());
         } else if (h->use_thin) {
             const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
-            { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
+            { Dev dt = d; dt.KT = h->thin_kc;
+          if (d.C == 10) thin_eval_kernel<true, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
+          else thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
             h->launches++;
             CUDA_TRY(h, cudaGetLastError());
         } else {
@@ -3868,7 +3876,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
+        { Dev dt = d; dt.KT = h->thin_kc;
+          if (d.C == 10) thin_eval_kernel<false, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
+          else thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {                                                 // generic dense stack
         StepArgs b = a;
         b.mode = MODE_EVAL_FIRST;
@@ -3884,7 +3894,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        { Dev dt = d; dt.KT = h->thin_kc; thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
+        { Dev dt = d; dt.KT = h->thin_kc;
+          if (d.C == 10) thin_eval_kernel<true, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
+          else thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {
         StepArgs b = a;
         b.mode = MODE_EVAL_STEP;
