@@ -410,6 +410,22 @@ __device__ void g_compute(const Dev &d, const float *sm, float *T, int k0, int c
 // backward: thread = 4 rows x 8 columns of the tile, all samples.
 // A thread's 8 columns are two runs of 4, N1/2 apart, so that a warp's float4 accesses
 // cover whole 128-byte lines.
+// Packed fp32 FMA (FFMA2 on sm_100): two IEEE fmas per instruction, bit-identical to two FFMAs.
+// The FMA pipe has the same peak either way (profiles/tools/ffma2_bench.cu: 73 TFLOP/s), but the
+// eval kernel is issue bound and FFMA2 halves the issue slots its multiply-adds take.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(f32x2 &acc, f32x2 a, f32x2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 // CN1 > 0 fixes the layer width (and B = 32, 256 threads) at compile time so that the strides
 // become immediates; CN1 = 0 reads them from the Dev.
 template <int CN1 = 0>
@@ -435,6 +451,11 @@ __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xba
         xr[i] = xbase + s * xstride;
     }
     const float *tc = T + 4 * cgi;
+    f32x2 a2[4][4];                                          // accumulators as column pairs
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a2[i][c] = pack2(acc[i][2 * c], acc[i][2 * c + 1]);
     for (int k = kb; k < ke; k += 4) {
         float xv[4][4];
 #pragma unroll
@@ -445,22 +466,22 @@ __device__ __forceinline__ void f_accumulate_fast(const Dev &d, const float *xba
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const float *tr = tc + (k + kk) * N1p;
-            const float4 t0 = *reinterpret_cast<const float4 *>(tr);
-            const float4 t1 = *reinterpret_cast<const float4 *>(tr + half);
+            const ulonglong2 t0 = *reinterpret_cast<const ulonglong2 *>(tr);        // (t0,t1) (t2,t3)
+            const ulonglong2 t1 = *reinterpret_cast<const ulonglong2 *>(tr + half);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float x = xv[i][kk];
-                acc[i][0] = fmaf(x, t0.x, acc[i][0]);
-                acc[i][1] = fmaf(x, t0.y, acc[i][1]);
-                acc[i][2] = fmaf(x, t0.z, acc[i][2]);
-                acc[i][3] = fmaf(x, t0.w, acc[i][3]);
-                acc[i][4] = fmaf(x, t1.x, acc[i][4]);
-                acc[i][5] = fmaf(x, t1.y, acc[i][5]);
-                acc[i][6] = fmaf(x, t1.z, acc[i][6]);
-                acc[i][7] = fmaf(x, t1.w, acc[i][7]);
+                const f32x2 x2 = pack2(xv[i][kk], xv[i][kk]);
+                ffma2(a2[i][0], x2, t0.x);
+                ffma2(a2[i][1], x2, t0.y);
+                ffma2(a2[i][2], x2, t1.x);
+                ffma2(a2[i][3], x2, t1.y);
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) unpack2(a2[i][c], acc[i][2 * c], acc[i][2 * c + 1]);
 }
 
 template <int CN1 = 0>
@@ -1909,27 +1930,29 @@ __global__ void __launch_bounds__(256, 2) eval_kernel(const __grid_constant__ De
             if (kl < cKT && k0 + kl < d.D) {
                 const float *xr = ((t & 1) ? X1 : X0) + kl;
                 float g[4][8];
+                f32x2 g2[4][4];                                  // column pairs, packed FMAs
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) g[j][c] = 0.f;
+                    for (int c = 0; c < 4; ++c) g2[j][c] = 0ull;
                 for (int s = 0; s < cnt; ++s) {
                     const float4 x = *reinterpret_cast<const float4 *>(xr + s * XS);
-                    const float4 d0 = *reinterpret_cast<const float4 *>(dp + s * cN1p);
-                    const float4 d1 = *reinterpret_cast<const float4 *>(dp + s * cN1p + half);
+                    const ulonglong2 d0 = *reinterpret_cast<const ulonglong2 *>(dp + s * cN1p);
+                    const ulonglong2 d1 = *reinterpret_cast<const ulonglong2 *>(dp + s * cN1p + half);
                     const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        g[j][0] = fmaf(xv[j], d0.x, g[j][0]);
-                        g[j][1] = fmaf(xv[j], d0.y, g[j][1]);
-                        g[j][2] = fmaf(xv[j], d0.z, g[j][2]);
-                        g[j][3] = fmaf(xv[j], d0.w, g[j][3]);
-                        g[j][4] = fmaf(xv[j], d1.x, g[j][4]);
-                        g[j][5] = fmaf(xv[j], d1.y, g[j][5]);
-                        g[j][6] = fmaf(xv[j], d1.z, g[j][6]);
-                        g[j][7] = fmaf(xv[j], d1.w, g[j][7]);
+                        const f32x2 x2 = pack2(xv[j], xv[j]);
+                        ffma2(g2[j][0], x2, d0.x);
+                        ffma2(g2[j][1], x2, d0.y);
+                        ffma2(g2[j][2], x2, d1.x);
+                        ffma2(g2[j][3], x2, d1.y);
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) unpack2(g2[j][c], g[j][2 * c], g[j][2 * c + 1]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (k0 + kl + j < d.D) {
