@@ -2387,15 +2387,38 @@ __global__ void __launch_bounds__(256) thin_eval_kernel(const __grid_constant__ 
             if (s0 < B) {
                 const float *x0 = xb + min(s0, B - 1) * XS, *x1 = xb + min(s0 + 1, B - 1) * XS;
                 const float *x2 = xb + min(s0 + 2, B - 1) * XS, *x3 = xb + min(s0 + 3, B - 1) * XS;
-                for (int k = lane; k < krows; k += 32) {
-                    const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
-                    const float *wr = wb + k * C;
+                if (CC && CC % 2 == 0) {
+                    // even compile-time class count: W row as 8-byte pairs, packed FMAs (FFMA2)
+                    f32x2 a2[4][CU / 2 + 1];
 #pragma unroll
-                    for (int c = 0; c < CU; ++c) {
-                        if (CC || c < C) {
-                            const float w = wr[c];
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(xv[i], w, acc[i][c]);
+                        for (int c = 0; c < CU / 2; ++c) a2[i][c] = pack2(acc[i][2 * c], acc[i][2 * c + 1]);
+                    for (int k = lane; k < krows; k += 32) {
+                        const f32x2 xx[4] = {pack2(x0[k], x0[k]), pack2(x1[k], x1[k]), pack2(x2[k], x2[k]), pack2(x3[k], x3[k])};
+                        const f32x2 *wr = reinterpret_cast<const f32x2 *>(wb + k * C);
+#pragma unroll
+                        for (int c = 0; c < CU / 2; ++c) {
+                            const f32x2 w2 = wr[c];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) ffma2(a2[i][c], xx[i], w2);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < CU / 2; ++c) unpack2(a2[i][c], acc[i][2 * c], acc[i][2 * c + 1]);
+                } else {
+                    for (int k = lane; k < krows; k += 32) {
+                        const float xv[4] = {x0[k], x1[k], x2[k], x3[k]};
+                        const float *wr = wb + k * C;
+#pragma unroll
+                        for (int c = 0; c < CU; ++c) {
+                            if (CC || c < C) {
+                                const float w = wr[c];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(xv[i], w, acc[i][c]);
+                            }
                         }
                     }
                 }
@@ -2794,6 +2817,9 @@ __device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            f32x2 acc2[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = 0ull;
             // the global loads of K step k0 + GT_K are in flight while step k0 is multiplied
             float ra[4], rb[4];
             auto fetch = [&](int k0) {
@@ -2827,15 +2853,21 @@ __device__ void gemm_tiled(int M, int N, int K, const float *A, long am, long ak
 #pragma unroll
                 for (int kk = 0; kk < GT_K; ++kk) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(smA + kk * GT_LD + ty * 4);
-                    const float4 b4 = *reinterpret_cast<const float4 *>(smB + kk * GT_LD + tx * 4);
+                    const ulonglong2 b2 = *reinterpret_cast<const ulonglong2 *>(smB + kk * GT_LD + tx * 4);
                     const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-                    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    for (int i = 0; i < 4; ++i) {                  // packed FMAs over column pairs
+                        const f32x2 a2 = pack2(av[i], av[i]);
+                        ffma2(acc2[i][0], a2, b2.x);
+                        ffma2(acc2[i][1], a2, b2.y);
+                    }
                 }
                 __syncthreads();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                unpack2(acc2[i][0], acc[i][0], acc[i][1]);
+                unpack2(acc2[i][1], acc[i][2], acc[i][3]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
