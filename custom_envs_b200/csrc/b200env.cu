@@ -2303,6 +2303,174 @@ __global__ void __launch_bounds__(256, 2) tc_eval_kernel(const __grid_constant__
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
+// ------------------------------------------------ eval kernel, bulk-copy operand pipeline
+// eval_kernel<., 64, 112> with the operand tiles moved by the copy engine instead of the threads:
+// per tile ONE cp.async.bulk for the contiguous 28 KB W1 tile and one per minibatch row piece
+// (448 B), completing on an mbarrier ("full"); the eight warps arrive on a second mbarrier
+// ("empty") when they have consumed a stage and warp 0 then refills it two tiles ahead.  This
+// removes the per-thread cp.async issue loops and the two CTA barriers per tile.
+namespace bk {
+constexpr int N1 = 64, KT = 112, B = 32, XS = 116;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+}  // namespace bk
+
+template <bool SECOND>
+__global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant__ Dev d,
+                                                           const __grid_constant__ StepArgs a) {
+    using namespace bk;
+    constexpr int PRODUCER = 7;       // the warp that refills the stages: idle in the backward tiles (kl >= KT)
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t full[2], empty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *const X0 = sm + d.ev_X0, *const W0 = sm + d.ev_W0;
+    const int xstep = d.ev_X1 - d.ev_X0, wstep = d.ev_W1 - d.ev_W0;   // stage s at X0 + s * xstep
+    float *misc = sm + d.off_misc;
+    int *idx_s = reinterpret_cast<int *>(sm + d.off_idx);
+    int *ys = reinterpret_cast<int *>(sm + d.off_y);
+    const int NT = d.ntiles;                                  // D / 112
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&empty[0], 8); mbar_init(&empty[1], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned fph = 0, eph = 0;                                // bit s: phase parity of stage s (warp-uniform)
+    const int e_end = a.e_begin + a.e_count;
+    for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        EnvScalars *sc = d.sc + e;
+        const float *wE = d.w + (size_t)e * d.Pp;
+        float *gout = d.gnext + (size_t)e * d.Pp;
+        const int *idx; int cnt;
+        current_batch(d, a, e, sc, idx, cnt);
+        __syncthreads();
+        if (tid < B) {
+            const int row = (tid < cnt) ? idx[tid] : 0;
+            idx_s[tid] = row;
+            ys[tid] = (tid < cnt) ? d.labels[row] : 0;
+        }
+        // rows the minibatch does not have (ragged last batch) read as zeros; the copies never touch them
+        for (int i = cnt * XS + tid; i < B * XS; i += blockDim.x) { X0[i] = 0.f; X0[xstep + i] = 0.f; }
+        for (int i = tid; i < d.tailP; i += blockDim.x) sm[d.off_tw + i] = wE[d.P1 + i];
+        __syncthreads();
+        // q = 0..NT-1: forward tiles (W1 and X), q = NT..2NT-1: backward tiles (X only); stage = q & 1
+        auto issue = [&](int q) {                              // producer warp only
+            const int s = q & 1, t = q < NT ? q : q - NT, k0 = t * KT;
+            const bool with_w = q < NT;
+            if (lane == 0) mbar_expect(&full[s], (with_w ? KT * N1 * 4 : 0) + cnt * KT * 4);
+            __syncwarp();
+            if (lane < cnt) bulk_load(X0 + s * xstep + lane * XS, d.X + (size_t)idx_s[lane] * d.Dp + k0, KT * 4, &full[s]);
+            if (with_w && lane == 0) bulk_load(W0 + s * wstep, wE + (size_t)k0 * N1, KT * N1 * 4, &full[s]);
+        };
+        auto wait_full = [&](int s) {
+            tc::mbar_wait(&full[s], (fph >> s) & 1u);
+            fph ^= 1u << s;
+        };
+        // This warp is done with the stage of tile q.  The producer warp then waits until every warp
+        // is and requests tile q + 2 into it; it runs the forward tiles a little behind the others
+        // because of that, which the one-tile lookahead absorbs.  (Requesting from inside its FMA
+        // loop instead, with mbarrier.test_wait, measured slower: profiles/r1_notes.md.)
+        auto release = [&](int q) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[q & 1]);
+            if (warp == PRODUCER) {
+                const int s = q & 1;
+                tc::mbar_wait(&empty[s], (eph >> s) & 1u);
+                eph ^= 1u << s;
+                if (q + 2 < 2 * NT) issue(q + 2);
+            }
+        };
+        if (warp == PRODUCER) { issue(0); issue(1); }
+
+        // ---- forward: Hpre = X . W1
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+        for (int t = 0; t < NT; ++t) {
+            wait_full(t & 1);
+            f_accumulate_fast<N1>(d, X0 + (t & 1) * xstep, XS, W0 + (t & 1) * wstep, KT, acc);
+            release(t);
+        }
+        __syncthreads();                                      // every warp is done with the W tiles
+        f_store_fast<N1>(d, sm, acc);                         // partials reduced through the W tiles
+        const float loss = d.C == 10 ? tail_eval<N1, 10>(d, sm, cnt) : tail_eval<N1, 0>(d, sm, cnt);
+
+        // ---- backward: tail gradient, then g = X^T . dPre tile by tile, straight to HBM
+        float gsum = 0.f;
+        for (int i = tid; i < d.tailP; i += blockDim.x) {
+            const float g = sm[d.off_tg + i];
+            gout[d.P1 + i] = g;
+            gsum += g;
+        }
+        const int rgi = tid >> 3, cgi = tid & 7, kl = rgi * 4;
+        constexpr int half = N1 >> 1;
+        const float *dp = sm + d.off_dP + 4 * cgi;
+        for (int t = 0; t < NT; ++t) {
+            const int q = NT + t, k0 = t * KT;
+            wait_full(q & 1);
+            if (kl < KT) {
+                const float *xr = X0 + (q & 1) * xstep + kl;
+                float g[4][8];
+                f32x2 g2[4][4];                                  // column pairs, packed FMAs
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) g2[j][c] = 0ull;
+                for (int s = 0; s < cnt; ++s) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xr + s * XS);
+                    const ulonglong2 d0 = *reinterpret_cast<const ulonglong2 *>(dp + s * N1);
+                    const ulonglong2 d1 = *reinterpret_cast<const ulonglong2 *>(dp + s * N1 + half);
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const f32x2 x2 = pack2(xv[j], xv[j]);
+                        ffma2(g2[j][0], x2, d0.x);
+                        ffma2(g2[j][1], x2, d0.y);
+                        ffma2(g2[j][2], x2, d1.x);
+                        ffma2(g2[j][3], x2, d1.y);
+                    }
+                }
+                release(q);                                   // the tile is in registers now
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) unpack2(g2[j][c], g[j][2 * c], g[j][2 * c + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float *dst = gout + (size_t)(k0 + kl + j) * N1 + 4 * cgi;
+                    *reinterpret_cast<float4 *>(dst) = make_float4(g[j][0], g[j][1], g[j][2], g[j][3]);
+                    *reinterpret_cast<float4 *>(dst + half) = make_float4(g[j][4], g[j][5], g[j][6], g[j][7]);
+                    gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
+                }
+            } else {                                          // the producer warp has no rows here
+                release(q);
+            }
+        }
+        if (!SECOND) continue;
+
+        // ---- scalars of the step (thread 0): history bookkeeping, reward, done, info
+        const double gtot = block_sum((double)gsum, reinterpret_cast<double *>(sm + d.off_red2));
+        if (tid == 0) step_scalars(d, a, sc, e, loss, gtot, misc);
+        __syncthreads();
+        const bool wrap = misc[4] != 0.f;
+        __syncthreads();
+        if (wrap) shuffle_order(d, e, sc);
+    }
+}
+
 // ------------------------------------------------ thin eval kernel: no hidden layer
 // Softmax regression (BASELINE config 3: 784 -> 10): logits Z = X.W + b with at most 16
 // classes.  There is almost no arithmetic (1 MFLOP per env); the kernel is the minibatch
@@ -3180,6 +3348,7 @@ struct b2e_env {
     int chunk_envs, obs_grid;
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
     bool eval_c;                     // eval_kernel instantiated for N1 = 64, KT = 112 (config 4)
+    bool eval_bulk;                  // ... and its bulk-copy / mbarrier pipelined form (B2E_EVAL_BULK=0 disables)
     int nchunks, eval_ctas_per_sm;   // B2E_CHUNKS experiment
     bool use_thin;                   // softmax regression: thin_eval_kernel
     size_t smem_thin;
@@ -3569,7 +3738,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (!h) return fail(nullptr, "b2e_create: out of host memory");
     h->cfg = *cfg;
     h->launches = 0;
-    h->nchunks = 1; h->eval_ctas_per_sm = 2; h->eval_c = false;
+    h->nchunks = 1; h->eval_ctas_per_sm = 2; h->eval_c = false; h->eval_bulk = false;
     h->dataset_bound = h->stream_bound = false;
     h->trace = false; h->tr_count = 0;
     for (auto &ev : h->tr) ev = nullptr;
@@ -3688,6 +3857,14 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             return bail("b2e_create: eval kernel does not fit shared memory");
         h->eval_c = d.N1 == 64 && d.N1p == 64 && d.KT == 112 && d.B == 32 && d.D % 112 == 0 && d.Dp == d.D &&
                     !getenv("B2E_EVAL_GENERIC");
+        h->eval_bulk = h->eval_c && d.kind == B2E_PROBLEM_SOFTMAX &&
+                       !(getenv("B2E_EVAL_BULK") && atoi(getenv("B2E_EVAL_BULK")) == 0);
+        if (h->eval_bulk &&
+            (cudaFuncSetAttribute(eval_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)h->smem_eval) != cudaSuccess ||
+             cudaFuncSetAttribute(eval_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)h->smem_eval) != cudaSuccess))
+            return bail("b2e_create: bulk eval kernel does not fit shared memory");
         h->nchunks = getenv("B2E_CHUNKS") ? atoi(getenv("B2E_CHUNKS")) : 1;
         if (h->nchunks > 1) {
             int prio_least = 0, prio_greatest = 0;
@@ -3703,6 +3880,12 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ev, eval_kernel<true>, 256, h->smem_eval) !=
                 cudaSuccess || occ_ev < 1)
             return bail("b2e_create: eval kernel does not fit an SM");
+        if (h->eval_bulk) {                                  // keep it only at the same residency
+            int occ_b = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, eval_bulk_kernel<true>, 256, h->smem_eval) !=
+                    cudaSuccess || occ_b < occ_ev)
+                h->eval_bulk = false;
+        }
         h->eval_grid = occ_ev * h->num_sms;
         h->eval_ctas_per_sm = getenv("B2E_EVAL_CTAS") ? atoi(getenv("B2E_EVAL_CTAS")) : occ_ev;
         h->chunk_envs = 4 * h->num_sms;
@@ -3852,6 +4035,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             const int cap = h->use_tc ? h->tc_grid : h->eval_grid;
             const int grid_ev = d.E < cap ? d.E : cap;
             if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
+            else if (h->eval_bulk) eval_bulk_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             h->launches++;
@@ -3928,7 +4112,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
-        if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        if (h->eval_bulk) eval_bulk_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        else if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
         { Dev dt = d; dt.KT = h->thin_kc;
@@ -3946,7 +4131,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
-        if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        if (h->eval_bulk) eval_bulk_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
         { Dev dt = d; dt.KT = h->thin_kc;
