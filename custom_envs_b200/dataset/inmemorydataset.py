@@ -1,49 +1,45 @@
 """In-memory data set with the reference's batching rules (dataset/inmemorydataset.py:11-38):
-contiguous slices of ``batch_size`` rows, ragged last batch, whole-array reshuffle at epoch
-end.  On the device path only ``features`` / ``targets`` / ``batch_size`` are read (the
-kernel keeps each env's row order itself); the Sequence protocol is kept for host users."""
-import math
-from collections import namedtuple
+batch ``k`` is rows ``[k*B, (k+1)*B)`` of the currently permuted arrays, the last batch is ragged,
+``on_epoch_end`` permutes both arrays with one shuffle of the GLOBAL numpy RNG.  On the device
+path only ``features`` / ``targets`` / ``batch_size`` are read (the kernels keep each env's row
+order themselves); the keras ``Sequence``-like protocol is kept for host users."""
+import collections
 
 import numpy as np
 
-BatchType = namedtuple('BatchType', ['features', 'labels'])
+BatchType = collections.namedtuple('BatchType', 'features labels')
 
 
 class DataSet:
-    """keras.utils.Sequence-like protocol: len / getitem / iteration / on_epoch_end."""
-
-    def __iter__(self):
-        return (self[i] for i in range(len(self)))
+    """len / getitem / iteration / on_epoch_end."""
 
     def on_epoch_end(self):
-        pass
+        """Hook run by the consumer when an epoch's iterator is exhausted."""
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self[k]
 
 
 class InMemoryDataSet(DataSet):
     def __init__(self, features, targets, batch_size=None):
-        assert len(features) == len(targets)
-        self.features = np.asarray(features)
-        self.targets = np.asarray(targets)
-        self.batch_size = len(self.features) if batch_size is None else int(batch_size)
+        self.features, self.targets = np.asarray(features), np.asarray(targets)
+        if len(self.features) != len(self.targets):
+            raise AssertionError('features and targets differ in length')
+        self.batch_size = int(batch_size) if batch_size is not None else len(self.features)
+
+    feature_shape = property(lambda self: self.features.shape[1:])
+    target_shape = property(lambda self: self.targets.shape[1:])
+
+    def __len__(self):
+        return -(-len(self.features) // self.batch_size)            # ceil
+
+    def __getitem__(self, k):
+        rows = slice(k * self.batch_size, (k + 1) * self.batch_size)
+        return BatchType(self.features[rows], self.targets[rows])
 
     def on_epoch_end(self):
         order = np.arange(len(self.features))
-        np.random.shuffle(order)                 # global RNG, as the reference does
-        self.features, self.targets = self.features[order], self.targets[order]
-
-    def __len__(self):
-        return math.ceil(len(self.features) / self.batch_size)
-
-    def __getitem__(self, idx):
-        begin = idx * self.batch_size
-        return BatchType(self.features[begin:begin + self.batch_size],
-                         self.targets[begin:begin + self.batch_size])
-
-    @property
-    def feature_shape(self):
-        return self.features.shape[1:]
-
-    @property
-    def target_shape(self):
-        return self.targets.shape[1:]
+        np.random.shuffle(order)                                    # global RNG, as the reference does
+        self.features = self.features[order]
+        self.targets = self.targets[order]

@@ -1,39 +1,34 @@
-"""The problem interface (reference problems/base_problem.py:8-73)."""
-from collections import namedtuple
+"""What an optimisation env asks of a problem (reference problems/base_problem.py:8-73): flat
+parameter / gradient vectors of length ``size``, a scalar loss, ``get()`` for the three at once,
+``next()`` to move to the following minibatch, ``reset()`` for a new episode."""
+import collections
 
-ProblemTuple = namedtuple('ProblemTuple', ['gradient', 'loss', 'parameters'])
+ProblemTuple = collections.namedtuple('ProblemTuple', 'gradient loss parameters')
+
+
+def _abstract(name):
+    def method(self, *args, **kwargs):
+        raise NotImplementedError('%s.%s' % (type(self).__name__, name))
+    method.__name__ = name
+    return method
 
 
 class BaseProblem:
+    reset = _abstract('reset')
+    get_gradient = _abstract('get_gradient')
+    get_loss = _abstract('get_loss')
+    get_parameters = _abstract('get_parameters')
+    set_parameters = _abstract('set_parameters')
+
     @classmethod
     def create(cls, *args, **kwargs):
         return cls(*args, **kwargs)
 
-    def reset(self):
-        raise NotImplementedError
-
-    def get_gradient(self):
-        raise NotImplementedError
-
-    def get_loss(self):
-        raise NotImplementedError
-
-    def get_parameters(self):
-        raise NotImplementedError
-
-    def set_parameters(self, parameters):
-        raise NotImplementedError
-
     def next(self):
-        """For problems that need to advance (next minibatch)."""
+        """Advance to the next minibatch; problems without data ignore it."""
 
     def get(self):
-        return ProblemTuple(self.get_gradient(), self.get_loss(), self.get_parameters())
+        return ProblemTuple(gradient=self.get_gradient(), loss=self.get_loss(), parameters=self.get_parameters())
 
-    @property
-    def size(self):
-        return len(self.get_parameters())
-
-    @property
-    def parameters(self):
-        return self.get_parameters()
+    parameters = property(lambda self: self.get_parameters())
+    size = property(lambda self: len(self.get_parameters()))

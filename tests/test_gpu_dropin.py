@@ -203,3 +203,49 @@ def test_device_optvecenv_matches_vecenv_oracle():
         assert np.allclose(rewards, want_r, rtol=1e-4, atol=1e-4) and np.array_equal(terminals, want_t)
         assert abs(infos[0]['batch_loss'] - want_i['batch_loss'][0]) < 1e-4
     vec.close()
+
+
+def test_device_wrappers_match_host_wrappers():
+    """DeviceHistoryWrapper / DeviceSubSetWrapper over the fused env batch give what the reference's
+    HistoryWrapper / SubSetWrapper (wrappers/optimizewrappers.py:9-70) give env by env, including the
+    history refill when an env finishes and is reset inside the step."""
+    import torch
+    from custom_envs import load_data
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    from custom_envs_b200.wrappers import DeviceHistoryWrapper, DeviceSubSetWrapper
+    data = load_data('iris', 32)
+    spec, envs, depth, episode = ProblemSpec('softmax', 4, (), 3), 3, 4, 5
+    make = partial(BatchedOptEnv, spec, data.features.astype(np.float32), data.targets.argmax(1), envs,
+                   batch_size=32, max_batches=episode, max_history=5, seeds=[1, 2, 3], init_seed=7)
+    plain, wrapped = make(), DeviceHistoryWrapper(make(), max_history=depth)
+    P, dim = plain.num_params, plain.obs_dim
+    ring = np.repeat(plain.reset().cpu().numpy()[None], depth, axis=0)          # [depth, rows, dim]
+    got = wrapped.reset()
+    assert tuple(got.shape) == (envs * P, depth, dim)
+    np.testing.assert_array_equal(got.cpu().numpy(), ring.transpose(1, 0, 2))
+    gen = torch.Generator(device=plain.device)
+    gen.manual_seed(0)
+    for t in range(2 * episode + 1):
+        actions = torch.rand(plain.num_rows, device=plain.device, generator=gen) * 3
+        obs, _, done, _ = plain.step(actions)
+        got, _, done_w, _ = wrapped.step(actions)
+        obs, done = obs.cpu().numpy(), done.cpu().numpy().astype(bool)
+        assert np.array_equal(done, done_w.cpu().numpy().astype(bool))
+        assert done.all() == ((t + 1) % episode == 0)
+        ring = np.concatenate([obs[None], ring[:-1]], axis=0)                    # newest first
+        for e in np.flatnonzero(done):                                           # wrapper.reset() of that env
+            ring[:, e * P:(e + 1) * P] = obs[e * P:(e + 1) * P]
+        np.testing.assert_array_equal(got.cpu().numpy(), ring.transpose(1, 0, 2))
+    # subset: rows of the named agents, env by env, in the order given
+    names = ['parameter-%d' % i for i in (12, 0, 7)]
+    sub = DeviceSubSetWrapper(make(), names)
+    rows_sorted = sorted('parameter-%d' % i for i in range(P))
+    full = sub.env.reset().cpu().numpy().copy()
+    picked = sub.reset().cpu().numpy()
+    want = np.stack([full[e * P + rows_sorted.index(n)] for e in range(envs) for n in names])
+    np.testing.assert_array_equal(picked, want)
+    step_full = sub.step(torch.ones(plain.num_rows, device=plain.device))[0].cpu().numpy()
+    want = np.stack([sub.env.obs.cpu().numpy()[e * P + rows_sorted.index(n)] for e in range(envs) for n in names])
+    np.testing.assert_array_equal(step_full, want)
+    for env in (plain, wrapped, sub):
+        env.close()
