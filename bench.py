@@ -191,6 +191,15 @@ def gpu_arm(args):
     device = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
+    numa_node = -1
+    if os.environ.get('B2E_NUMA_BIND', '1') != '0':
+        # one process per GPU: run on (and first-touch the pinned staging buffers of the e2e
+        # path in) the NUMA node the GPU hangs off; no-op where the platform reports none
+        from custom_envs_b200.sharding import bind_to_gpu_numa, device_pci_bus_id
+        try:
+            numa_node = bind_to_gpu_numa(device_pci_bus_id(local))
+        except (AttributeError, RuntimeError):
+            numa_node = -1
     envs = args.envs
     feats, labels = synthetic_data()
     # envs shard by index: rank r owns envs [r*envs, (r+1)*envs); seeds follow the global index
@@ -307,7 +316,8 @@ def gpu_arm(args):
                        'envs_done_last_step': done_total, 'parallelism': 'env-index shards, dp%d' % world},
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
-                    'api': 'DeviceOptVecEnv.step(numpy actions) -> numpy states/rewards/dones + infos'},
+                    'api': 'DeviceOptVecEnv.step(numpy actions) -> numpy states/rewards/dones + infos',
+                    'numa_node_bound': numa_node},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

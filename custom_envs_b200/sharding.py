@@ -41,3 +41,53 @@ def gather_env_stats(local_stats, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([part[:n] for part, n in zip(parts, counts)], dim=0)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(pci_bus_id, sysfs='/sys'):
+    """NUMA node the GPU's PCIe root hangs off (-1 when the platform does not say, e.g. in a
+    VM).  ``pci_bus_id`` as CUDA prints it: ``0000:1B:00.0`` (domain may have 8 hex digits)."""
+    import os
+    domain, _, rest = pci_bus_id.lower().partition(':')
+    path = os.path.join(sysfs, 'bus/pci/devices', '%s:%s' % (domain[-4:], rest), 'numa_node')
+    try:
+        with open(path) as fh:
+            return int(fh.read().strip())
+    except (OSError, ValueError):
+        return -1
+
+
+def device_pci_bus_id(index):
+    """``domain:bus:device.0`` of CUDA device ``index`` (what sysfs names the GPU)."""
+    props = torch.cuda.get_device_properties(index)
+    return '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+
+
+def bind_to_gpu_numa(pci_bus_id, sysfs='/sys'):
+    """Pin this process to the CPUs of the GPU's NUMA node, so that the pinned staging
+    buffers of the host-facing VecEnv (12.5 GB of observations per step at config 4) are
+    first-touched on the memory next to the GPU's PCIe root and the copy threads run there.
+    Call before allocating pinned memory.  Returns the node, or -1 if nothing was changed."""
+    import os
+    node = gpu_numa_node(pci_bus_id, sysfs)
+    if node < 0 or not hasattr(os, 'sched_setaffinity'):
+        return -1
+    try:
+        with open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return -1
+        os.sched_setaffinity(0, allowed)
+    except OSError:
+        return -1
+    return node

@@ -69,6 +69,40 @@ class LazyInfos:
                 yield info
 
 
+_COPY_POOL = None
+_COPY_CHUNK = 1 << 23            # float32 elements per staged chunk (32 MB)
+
+
+def _copy_pool():
+    """Host threads that stage numpy inputs into pinned memory.  Own pool, because torchrun
+    exports OMP_NUM_THREADS=1 and would make torch's host copy single-threaded."""
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+        _COPY_POOL = ThreadPoolExecutor(max(1, min(8, cpus)), thread_name_prefix='b2e-stage')
+    return _COPY_POOL
+
+
+def stage_to_device(src, host, dev, chunk=_COPY_CHUNK):
+    """numpy ``src`` -> pinned ``host`` -> device ``dev`` (1-D, same length).  Chunks are copied
+    into the pinned buffer by the pool (numpy releases the GIL) and each chunk's
+    host->device copy is queued as soon as it is staged, so the two overlap."""
+    count = src.shape[0]
+    staged = host.numpy()
+    if count <= chunk:
+        np.copyto(staged, src)
+        dev.copy_(host, non_blocking=True)
+        return
+    cuts = list(range(0, count, chunk)) + [count]
+    pool = _copy_pool()
+    jobs = [pool.submit(np.copyto, staged[lo:hi], src[lo:hi]) for lo, hi in zip(cuts, cuts[1:])]
+    for job, lo, hi in zip(jobs, cuts, cuts[1:]):
+        job.result()
+        dev[lo:hi].copy_(host[lo:hi], non_blocking=True)
+
+
 class DeviceOptVecEnv(VecEnv):
     """VecEnv over a ``BatchedOptEnv``: numpy in, numpy out, state stays in HBM.
 
@@ -110,12 +144,11 @@ class DeviceOptVecEnv(VecEnv):
         self._rew_host = torch.empty(envs, dtype=torch.float32, **pin)
         self._done_host = torch.empty(envs, dtype=torch.uint8, **pin)
         self._info_host = torch.empty((envs, 16), dtype=torch.float64, **pin)
-        # the VecEnv surface repeats reward / done once per agent row (optvecenv.py:43-45); at
-        # 2e8 rows that is cheaper as a device expand + PCIe copy than as np.repeat on the host
-        self._rew_rows = torch.empty(rows, dtype=torch.float32, device=dev)
-        self._done_rows = torch.empty(rows, dtype=torch.bool, device=dev)
-        self._rew_rows_host = torch.empty(rows, dtype=torch.float32, **pin)
-        self._done_rows_host = torch.empty(rows, dtype=torch.bool, **pin)
+        # the VecEnv surface repeats reward / done once per agent row (optvecenv.py:43-45): host
+        # threads expand the per-env values while the observation copy is still on the wire
+        self._rew_rows_np = np.empty(rows, dtype=np.float32)
+        self._done_rows_np = np.empty(rows, dtype=np.bool_)
+        self._scalars_event = torch.cuda.Event()
         self._event = torch.cuda.Event()
 
     def _states(self):
@@ -123,11 +156,37 @@ class DeviceOptVecEnv(VecEnv):
         return states.copy() if self.copy_outputs else states
 
     def _row_outputs(self):
-        """(rewards[rows], terminals[rows]): views of pinned buffers unless copy_outputs."""
-        rewards, terminals = self._rew_rows_host.numpy(), self._done_rows_host.numpy()
+        """(rewards[rows], terminals[rows]); buffers reused by the next step unless copy_outputs."""
         if self.copy_outputs:
-            return rewards.copy(), terminals.copy()
-        return rewards, terminals
+            return self._rew_rows_np.copy(), self._done_rows_np.copy()
+        return self._rew_rows_np, self._done_rows_np
+
+    def _expand_rows(self):
+        envs, agents = self.env.num_envs, self.env.num_params
+        reward = self._rew_host.numpy()
+        done = self._done_host.numpy().astype(np.bool_)
+        rew_rows = self._rew_rows_np.reshape(envs, agents)
+        done_rows = self._done_rows_np.reshape(envs, agents)
+
+        def fill(lo, hi):
+            rew_rows[lo:hi] = reward[lo:hi, None]
+            done_rows[lo:hi] = done[lo:hi, None]
+
+        if envs * agents <= _COPY_CHUNK:
+            fill(0, envs)
+            return
+        pool = _copy_pool()
+        cuts = np.linspace(0, envs, min(envs, 4 * pool._max_workers) + 1).astype(np.int64)
+        for job in [pool.submit(fill, int(lo), int(hi)) for lo, hi in zip(cuts, cuts[1:])]:
+            job.result()
+
+    def _wait_outputs(self):
+        """Block until the step's outputs are in host memory: the per-env scalars arrive
+        first and are expanded per agent row while the observation copy is in flight."""
+        self._scalars_event.synchronize()
+        self._expand_rows()
+        self._event.synchronize()
+        self.waiting = False
 
     def reset(self):
         obs = self.env.reset()
@@ -138,26 +197,20 @@ class DeviceOptVecEnv(VecEnv):
     def step_async(self, actions):
         actions = np.ascontiguousarray(np.asarray(actions, np.float32).reshape(-1))
         assert actions.size == self.num_envs
-        self._act_host.copy_(self._torch.from_numpy(actions))        # multi-threaded host copy
-        self._act_dev.copy_(self._act_host, non_blocking=True)
+        stage_to_device(actions, self._act_host, self._act_dev)
         obs, reward, done, info = self.env.step(
             self._act_dev, obs_out=self._obs_host if self.direct_host_obs else None)
-        envs, agents = self.env.num_envs, self.env.num_params
-        self._rew_rows.view(envs, agents).copy_(reward[:, None].expand(envs, agents))
-        self._done_rows.view(envs, agents).copy_(done[:, None].expand(envs, agents))
         self._rew_host.copy_(reward, non_blocking=True)
         self._done_host.copy_(done, non_blocking=True)
         self._info_host.copy_(info, non_blocking=True)
-        self._rew_rows_host.copy_(self._rew_rows, non_blocking=True)
-        self._done_rows_host.copy_(self._done_rows, non_blocking=True)
+        self._scalars_event.record(self._torch.cuda.current_stream(self.env.device))
         if not self.direct_host_obs:
             self._obs_host.copy_(obs, non_blocking=True)
         self._event.record(self._torch.cuda.current_stream(self.env.device))
         self.waiting = True
 
     def step_wait(self):
-        self._event.synchronize()
-        self.waiting = False
+        self._wait_outputs()
         agents = self.env.num_params
         states = self._states()
         rewards, terminals = self._row_outputs()
@@ -326,8 +379,7 @@ class OptVecEnv(VecEnv):
             states, rewards, terminals, infos = self._impl.step_wait()
         else:
             impl = self._impl
-            impl._event.synchronize()
-            impl.waiting = False
+            impl._wait_outputs()
             agents = impl.env.num_params
             states = impl._states()
             reward_env = impl._rew_host.numpy()
