@@ -256,8 +256,12 @@ def gpu_arm(args):
     vec.step(host_actions)                                   # warm the pinned buffers
     barrier()
     t0 = time.perf_counter()
+    e2e_marks, e2e_phases = [t0], {}
     for _ in range(e2e_steps):
         states, rewards, dones, infos = vec.step(host_actions)
+        e2e_marks.append(time.perf_counter())
+        for name, ms_p in vec.last_timing.items():
+            e2e_phases[name] = e2e_phases.get(name, 0.0) + ms_p / e2e_steps
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -317,7 +321,9 @@ def gpu_arm(args):
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
                     'api': 'DeviceOptVecEnv.step(numpy actions) -> numpy states/rewards/dones + infos',
-                    'numa_node_bound': numa_node},
+                    'numa_node_bound': numa_node,
+                    'host_phase_ms': {k: round(v, 1) for k, v in e2e_phases.items()},
+                    'ms_each_step': [round(1e3 * (b - a), 1) for a, b in zip(e2e_marks, e2e_marks[1:])]},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
@@ -346,7 +352,7 @@ def main():
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     parser.add_argument('--envs', type=int, default=4096, help='envs per GPU')
     parser.add_argument('--row-order', default='lexicographic', choices=['lexicographic', 'natural'])
-    parser.add_argument('--e2e-steps', type=int, default=3)
+    parser.add_argument('--e2e-steps', type=int, default=5)
     args = parser.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

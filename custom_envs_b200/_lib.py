@@ -23,7 +23,11 @@ EXPORTS = (
     'b2e_abi_version', 'b2e_create', 'b2e_destroy', 'b2e_last_error', 'b2e_num_params',
     'b2e_obs_dim', 'b2e_history_depth', 'b2e_bind_dataset', 'b2e_set_index_stream', 'b2e_reset', 'b2e_step',
     'b2e_eval', 'b2e_get_state', 'b2e_set_state', 'b2e_get_batch_indices', 'b2e_next_batch',
-    'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count')
+    'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count',
+    # data front-end (include/b200data.h)
+    'b2d_last_error', 'b2d_resize_nearest', 'b2d_minmax_workspace', 'b2d_column_minmax',
+    'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot')
+DTYPE_U8, DTYPE_I32, DTYPE_F32, DTYPE_F64 = range(4)
 
 
 class Config(ctypes.Structure):
@@ -75,6 +79,18 @@ def load():
     lib.b2e_get_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32]
     lib.b2e_launch_count.argtypes = [vp]
     lib.b2e_launch_count.restype = ctypes.c_int64
+    i64 = ctypes.c_int64
+    lib.b2d_last_error.argtypes = []
+    lib.b2d_last_error.restype = ctypes.c_char_p
+    lib.b2d_resize_nearest.argtypes = [vp, i32, i64, i32, i32, vp, vp, i32, i32, vp, vp]
+    lib.b2d_minmax_workspace.argtypes = [i32]
+    lib.b2d_minmax_workspace.restype = usize
+    lib.b2d_column_minmax.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp]
+    lib.b2d_normalize.argtypes = [vp, i32, i64, i32, vp, vp, vp, i32, i64, vp]
+    lib.b2d_rank_workspace.argtypes = []
+    lib.b2d_rank_workspace.restype = usize
+    lib.b2d_label_ranks.argtypes = [vp, i64, vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
+    lib.b2d_onehot.argtypes = [vp, i64, i32, vp, i32, vp, vp]
     if lib.b2e_abi_version() != 2:
         raise B200EnvError('libb200env.so ABI version mismatch')
     _lib = lib

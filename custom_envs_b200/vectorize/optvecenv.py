@@ -9,6 +9,7 @@ Two implementations behind one class:
 * generic path -- anything else (e.g. the reference's StubEnv tests) runs thread-per-env
   through ``ThreadVecEnv`` + ``OptEnvRunner`` exactly as the reference does.
 """
+import time
 from itertools import chain
 
 import numpy as np
@@ -129,6 +130,7 @@ class DeviceOptVecEnv(VecEnv):
         self.direct_host_obs = bool(direct_host_obs)
         self.waiting = False
         self.closed = False
+        self.last_timing = {}
         if observation_space is None:
             observation_space, _ = utils_env.get_obs_version((batched_env.num_params,),
                                                              batched_env.max_history, 3)
@@ -183,10 +185,18 @@ class DeviceOptVecEnv(VecEnv):
     def _wait_outputs(self):
         """Block until the step's outputs are in host memory: the per-env scalars arrive
         first and are expanded per agent row while the observation copy is in flight."""
+        clock = time.perf_counter
+        t0 = clock()
         self._scalars_event.synchronize()
+        t1 = clock()
         self._expand_rows()
+        t2 = clock()
         self._event.synchronize()
+        t3 = clock()
         self.waiting = False
+        # host-side phases of the last step in ms (where the end-to-end time goes)
+        self.last_timing.update(wait_step=1e3 * (t1 - t0), expand_rows=1e3 * (t2 - t1),
+                                wait_obs_copy=1e3 * (t3 - t2))
 
     def reset(self):
         obs = self.env.reset()
@@ -197,7 +207,9 @@ class DeviceOptVecEnv(VecEnv):
     def step_async(self, actions):
         actions = np.ascontiguousarray(np.asarray(actions, np.float32).reshape(-1))
         assert actions.size == self.num_envs
+        t0 = time.perf_counter()
         stage_to_device(actions, self._act_host, self._act_dev)
+        t1 = time.perf_counter()
         obs, reward, done, info = self.env.step(
             self._act_dev, obs_out=self._obs_host if self.direct_host_obs else None)
         self._rew_host.copy_(reward, non_blocking=True)
@@ -208,6 +220,7 @@ class DeviceOptVecEnv(VecEnv):
             self._obs_host.copy_(obs, non_blocking=True)
         self._event.record(self._torch.cuda.current_stream(self.env.device))
         self.waiting = True
+        self.last_timing = {'stage_actions': 1e3 * (t1 - t0), 'queue_step': 1e3 * (time.perf_counter() - t1)}
 
     def step_wait(self):
         self._wait_outputs()

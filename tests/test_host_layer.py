@@ -63,9 +63,10 @@ class ArrayStubEnv(StubEnv):
 # ------------------------------------------------------------------ C ABI presence
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
-    header = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'b200env.h')).read()
+    include = os.path.join(os.path.dirname(__file__), '..', 'include')
+    header = ''.join(open(os.path.join(include, name)).read() for name in sorted(os.listdir(include)))
     import re
-    declared = set(re.findall(r'\b(b2e_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(b2[ed]_[a-z_]+)\s*\(', header))
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None

@@ -17,7 +17,7 @@ import torch
 
 from oracle import optenv_oracle as orc
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz')))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', 'opt*.npz')))
 
 
 def load_fixture(path):
