@@ -22,7 +22,35 @@ def synthetic_classification(num_rows, num_features, num_classes, seed=0):
     return features, labels
 
 
-def load_data(name='iris', batch_size=32, num_of_labels=None):
+def _load_on_device(name, batch_size, num_of_labels, device):
+    """Raw bytes / raw table -> device front-end -> ``DeviceDataSet`` (no float data on the host)."""
+    from custom_envs_b200.data import device_frontend as front
+    from custom_envs_b200.dataset import DeviceDataSet
+    if name == 'iris':
+        from sklearn import datasets
+        iris = datasets.load_iris()
+        features = front.normalize(iris.data, device=device)
+        ranks, unique = front.label_ranks(iris.target, device=device)
+    elif name in _SYNTHETIC_ROWS:
+        warnings.warn('data set %r is not available offline; using synthetic 28x28 uint8 images '
+                      'of its shape, down-sampled and normalised on the device' % name)
+        rng = np.random.RandomState(0)
+        images = rng.randint(0, 256, size=(_SYNTHETIC_ROWS[name], 28, 28)).astype(np.uint8)
+        features, ranks, unique = front.image_dataset(images, rng.randint(0, 10, size=len(images)),
+                                                      (7, 7), device=device)
+    else:
+        raise RuntimeError('No such data set named: {}'.format(name))
+    num = unique if num_of_labels is None else int(num_of_labels)
+    if unique > num:
+        raise IndexError('more distinct labels (%d) than num_of_labels (%d)' % (unique, num))
+    return DeviceDataSet(features, ranks, batch_size, num)
+
+
+def load_data(name='iris', batch_size=32, num_of_labels=None, device=None):
+    """``device=None`` prepares the arrays on the host exactly as the reference does;
+    ``device='cuda:0'`` uploads the raw data and prepares it with the CUDA front-end."""
+    if device is not None:
+        return _load_on_device(name, batch_size, num_of_labels, device)
     if name == 'iris':
         from sklearn import datasets
         iris = datasets.load_iris()

@@ -43,3 +43,28 @@ class InMemoryDataSet(DataSet):
         np.random.shuffle(order)                                    # global RNG, as the reference does
         self.features = self.features[order]
         self.targets = self.targets[order]
+
+
+class DeviceDataSet(DataSet):
+    """A data set prepared by the device front-end (custom_envs_b200/data/device_frontend.py):
+    ``features`` float32 [N, D] and ``targets`` int32 label ranks [N] are CUDA tensors that the
+    env kernels bind directly.  Batches are device slices; ``on_epoch_end`` is a no-op here
+    because the kernels keep every env's row order themselves."""
+    on_device = True
+
+    def __init__(self, features, targets, batch_size=None, num_classes=None):
+        if len(features) != len(targets):
+            raise AssertionError('features and targets differ in length')
+        self.features, self.targets = features, targets
+        self.batch_size = int(batch_size) if batch_size is not None else len(features)
+        self.num_classes = int(num_classes if num_classes is not None else int(targets.max().item()) + 1)
+
+    feature_shape = property(lambda self: tuple(self.features.shape[1:]))
+    target_shape = property(lambda self: (self.num_classes,))
+
+    def __len__(self):
+        return -(-len(self.features) // self.batch_size)
+
+    def __getitem__(self, k):
+        rows = slice(k * self.batch_size, (k + 1) * self.batch_size)
+        return BatchType(self.features[rows], self.targets[rows])

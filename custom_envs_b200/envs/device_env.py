@@ -48,7 +48,7 @@ class DeviceEnvFront(BaseMultiEnvironment):
 
     def fuse_key(self):
         feats, targs = self.model.device_arrays()
-        data = None if feats is None else (feats.shape, float(feats.sum()), float(np.sum(targs)))
+        data = None if feats is None else (tuple(feats.shape), float(feats.sum()), float(targs.sum()))
         return (type(self).__name__, self.model.spec, data, tuple(sorted(self.backend_kwargs().items())))
 
     def seed(self, seed=None):

@@ -107,6 +107,11 @@ class OptimizeNN(_DeviceProblem):
                     'fused kernel; pass layers=(hidden_units,) or a model_fn with a .layers tuple')
             layers = (256, 256)                 # utils/utils_tf.py:74
         layers = tuple(int(h) for h in layers)
+        if getattr(data_set, 'on_device', False):
+            # prepared by the device front-end: float32 rows and int32 label ranks already in HBM
+            self.spec = ProblemSpec('softmax', data_set.features.shape[1], layers, data_set.num_classes)
+            self._features, self._labels = data_set.features, data_set.targets
+            return
         features = np.asarray(data_set.features)
         targets = np.asarray(data_set.targets)
         num_outputs = targets.shape[1] if targets.ndim == 2 else int(targets.max()) + 1

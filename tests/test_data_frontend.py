@@ -166,3 +166,28 @@ def test_device_dataset_feeds_the_env_like_the_host_dataset():
         env.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_load_data_on_device_equals_host_preparation():
+    """load_data(name, device=...) (raw table -> CUDA front-end) against the host path of the
+    same loader, and an OptimizeNN env built on the device data set."""
+    from custom_envs_b200.data import load_data
+    host = load_data('iris', batch_size=32)
+    dev_set = load_data('iris', batch_size=32, device='cuda:0')
+    assert len(dev_set) == len(host) == 5 and dev_set.num_classes == 3
+    assert np.array_equal(dev_set.features.cpu().numpy(), host.features.astype(np.float32))
+    assert np.array_equal(dev_set.targets.cpu().numpy(), host.targets.argmax(axis=1))
+    from custom_envs_b200.envs.multioptlrs import MultiOptLRs
+    outs = []
+    action = {'parameter-%d' % i: np.array([1.0 + 0.1 * i], np.float32) for i in range(15)}
+    for data_set in (host, dev_set):
+        env = MultiOptLRs(problem='nn', max_batches=10, problem_kwargs=dict(layers=(), data_set=data_set))
+        env.seed(3)
+        env.reset()
+        env.model.set_parameters(np.linspace(-0.5, 0.5, 15))
+        for _ in range(2):
+            state, reward, _, info = env.step(action)
+        outs.append((np.stack([state[key] for key in sorted(state)]), reward, info['batch_loss']))
+        env.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]

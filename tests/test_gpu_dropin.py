@@ -249,3 +249,39 @@ def test_device_wrappers_match_host_wrappers():
     np.testing.assert_array_equal(step_full, want)
     for env in (plain, wrapped, sub):
         env.close()
+
+
+def test_device_rollout_matches_a_manual_loop():
+    """Policy in the loop on the device: chunked policy evaluation + env.step equals the same
+    loop written out with whole-matrix policy calls."""
+    import torch
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy, device_rollout
+    rng = np.random.RandomState(0)
+    feats = rng.uniform(size=(150, 4)).astype(np.float32)
+    labels = (np.arange(150) % 3).astype(np.int32)
+    torch.manual_seed(0)
+    policy = SharedMlpPolicy(15).to('cuda:0')
+    mean_only = lambda obs: policy.pi(obs).squeeze(-1)            # noqa: E731 (deterministic)
+    results = []
+    for chunked in (True, False):
+        env = BatchedOptEnv(ProblemSpec('softmax', 4, (), 3), feats, labels, 8, batch_size=32,
+                            max_batches=6, seeds=list(range(8)), init_seed=5)
+        env.reset()
+        if chunked:
+            seen = []
+            returns, finished = device_rollout(env, mean_only, 7, row_chunk=32,
+                                               on_step=lambda t, o, r, d, i: seen.append(o.clone()))
+            results.append((returns.cpu().numpy(), finished, seen[-1].cpu().numpy()))
+        else:
+            returns, finished, obs = torch.zeros(8, dtype=torch.float64, device='cuda:0'), 0, env.obs
+            with torch.no_grad():
+                for _ in range(7):
+                    obs, reward, done, _ = env.step(mean_only(obs).clamp(-4.0, 6.0))
+                    returns += reward
+                    finished += int(done.sum())
+            results.append((returns.cpu().numpy(), finished, obs.cpu().numpy()))
+        env.close()
+    assert results[0][1] == results[1][1] == 8            # every env ended once (max_batches=6)
+    assert np.allclose(results[0][0], results[1][0], rtol=1e-6)
+    assert np.allclose(results[0][2], results[1][2], rtol=1e-5, atol=1e-6)
