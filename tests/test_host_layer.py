@@ -263,3 +263,15 @@ def test_gym_ids_registered():
     if not hasattr(gym, '__standin__'):
         pytest.skip('real gym present')
     assert 'MultiOptLRs-v0' in gym_standin._REGISTRY
+
+
+def test_stage_to_device_chunks_cover_the_vector():
+    """The staging helper of the host-facing VecEnv (numpy -> pinned -> device in chunks handled by
+    the library's own threads) on CPU tensors: ragged last chunk, single chunk, one element."""
+    import torch
+    from custom_envs_b200.vectorize.optvecenv import stage_to_device
+    for count, chunk in [(100003, 4096), (4096, 4096), (1, 8), (12345, 1 << 23)]:
+        src = np.random.RandomState(count).rand(count).astype(np.float32)
+        host, dev = torch.zeros(count), torch.zeros(count)
+        stage_to_device(src, host, dev, chunk=chunk)
+        assert np.array_equal(dev.numpy(), src) and np.array_equal(host.numpy(), src)

@@ -51,3 +51,28 @@ def test_gather_env_stats_gloo_world2(tmp_path):
 def test_gather_is_identity_without_process_group():
     stats = torch.ones(3, 2)
     assert gather_env_stats(stats) is stats
+
+
+def test_numa_binding_reads_the_gpu_node_from_sysfs(tmp_path):
+    """bind_to_gpu_numa against a fake sysfs tree: GPU on node 1 whose CPUs include the ones this
+    process may run on; a platform that reports no node (-1, VMs) changes nothing."""
+    from custom_envs_b200.sharding import _parse_cpulist, bind_to_gpu_numa, gpu_numa_node
+    assert _parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    allowed = sorted(os.sched_getaffinity(0))
+    keep = allowed[:max(1, len(allowed) // 2)]
+    pci = tmp_path / 'bus/pci/devices/0000:1b:00.0'
+    pci.mkdir(parents=True)
+    (pci / 'numa_node').write_text('1\n')
+    node = tmp_path / 'devices/system/node/node1'
+    node.mkdir(parents=True)
+    (node / 'cpulist').write_text(','.join(str(c) for c in keep) + ',4093-4095\n')
+    assert gpu_numa_node('00000000:1B:00.0', str(tmp_path)) == 1          # CUDA's spelling of the id
+    try:
+        assert bind_to_gpu_numa('0000:1b:00.0', str(tmp_path)) == 1
+        assert sorted(os.sched_getaffinity(0)) == keep
+    finally:
+        os.sched_setaffinity(0, allowed)
+    (pci / 'numa_node').write_text('-1\n')
+    assert bind_to_gpu_numa('0000:1b:00.0', str(tmp_path)) == -1
+    assert bind_to_gpu_numa('0000:ff:00.0', str(tmp_path)) == -1          # unknown device
+    assert sorted(os.sched_getaffinity(0)) == allowed
