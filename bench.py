@@ -253,7 +253,8 @@ def gpu_arm(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     vec = DeviceOptVecEnv(env)
     host_actions = np.random.RandomState(3 + rank).uniform(0, 3, size=(env.num_rows, 1)).astype(np.float32)
-    vec.step(host_actions)                                   # warm the pinned buffers
+    for _ in range(3):                                       # warm the pinned buffers (first touches
+        vec.step(host_actions)                               # of 14 GB of host memory per rank)
     barrier()
     t0 = time.perf_counter()
     e2e_marks, e2e_phases = [t0], {}
