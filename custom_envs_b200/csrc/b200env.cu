@@ -2326,13 +2326,22 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
 }
 }  // namespace bk
 
-template <bool SECOND>
+// FUSED (first eval only): the update w_t = w_{t-1} - g0 * lr(action) (update_kernel's work) happens in
+// the backward epilogue while the gradient tile is still in registers: the W1 tile is bulk-copied
+// a second time into the W stage that idles during the backward pass (an L2 hit mostly: this CTA
+// read it a few microseconds ago), so g0 is never written, and w / g0 are not re-read from HBM by a
+// separate kernel.  Saves 3 of the step's 35 words per parameter and one launch -- but no time:
+// measured 1.54 ms against 0.84 + 0.70 ms for the two kernels (profiles/r1_notes.md): the epilogue
+// issues about as many instructions per tile as the FMA loop, and the eval kernel is issue bound,
+// while the separate update kernel runs at 90 % of the HBM rate.  Opt-in (B2E_FUSE_UPDATE=1).
+template <bool SECOND, bool FUSED = false>
 __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant__ Dev d,
                                                            const __grid_constant__ StepArgs a) {
     using namespace bk;
     constexpr int PRODUCER = 7;       // the warp that refills the stages: idle in the backward tiles (kl >= KT)
     extern __shared__ __align__(16) float sm[];
-    __shared__ __align__(8) uint64_t full[2], empty[2];
+    __shared__ __align__(8) uint64_t full[2], empty[2], wfull[2];
+    static_assert(!(SECOND && FUSED), "the update belongs to the first eval");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *const X0 = sm + d.ev_X0, *const W0 = sm + d.ev_W0;
     const int xstep = d.ev_X1 - d.ev_X0, wstep = d.ev_W1 - d.ev_W0;   // stage s at X0 + s * xstep
@@ -2343,15 +2352,21 @@ __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant
     if (tid == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
         mbar_init(&empty[0], 8); mbar_init(&empty[1], 8);
+        mbar_init(&wfull[0], 1); mbar_init(&wfull[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    unsigned fph = 0, eph = 0;                                // bit s: phase parity of stage s (warp-uniform)
+    unsigned fph = 0, eph = 0, wph = 0;                       // bit s: phase parity of stage s (warp-uniform)
     const int e_end = a.e_begin + a.e_count;
     for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
         EnvScalars *sc = d.sc + e;
         const float *wE = d.w + (size_t)e * d.Pp;
         float *gout = d.gnext + (size_t)e * d.Pp;
+        float *wOut = d.w + (size_t)e * d.Pp;                                                  // FUSED: updated in place
+        float *rw = d.ringw + ((size_t)e * d.H + (sc->head + 1) % d.H) * d.Pp;                 // FUSED: adjusted weights
+        const float *act = a.actions + (size_t)e * d.P;
+        float s_absw = 0.f;
+        double s_lr = 0.0, s_lr2 = 0.0;
         const int *idx; int cnt;
         current_batch(d, a, e, sc, idx, cnt);
         __syncthreads();
@@ -2373,6 +2388,16 @@ __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant
             if (lane < cnt) bulk_load(X0 + s * xstep + lane * XS, d.X + (size_t)idx_s[lane] * d.Dp + k0, KT * 4, &full[s]);
             if (with_w && lane == 0) bulk_load(W0 + s * wstep, wE + (size_t)k0 * N1, KT * N1 * 4, &full[s]);
         };
+        // FUSED: old weights of backward tile q into the idle W stage (own barrier: the first two are
+        // requested only after the forward partials have left the W stages)
+        auto issue_w = [&](int q) {                            // producer warp only
+            const int s = q & 1, k0 = (q - NT) * KT;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect(&wfull[s], KT * N1 * 4);
+                bulk_load(W0 + s * wstep, wE + (size_t)k0 * N1, KT * N1 * 4, &wfull[s]);
+            }
+        };
         auto wait_full = [&](int s) {
             tc::mbar_wait(&full[s], (fph >> s) & 1u);
             fph ^= 1u << s;
@@ -2388,7 +2413,10 @@ __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant
                 const int s = q & 1;
                 tc::mbar_wait(&empty[s], (eph >> s) & 1u);
                 eph ^= 1u << s;
-                if (q + 2 < 2 * NT) issue(q + 2);
+                if (q + 2 < 2 * NT) {
+                    issue(q + 2);
+                    if (FUSED && q >= NT) issue_w(q + 2);
+                }
             }
         };
         if (warp == PRODUCER) { issue(0); issue(1); }
@@ -2406,13 +2434,26 @@ __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant
         }
         __syncthreads();                                      // every warp is done with the W tiles
         f_store_fast<N1>(d, sm, acc);                         // partials reduced through the W tiles
+        if (FUSED && warp == PRODUCER) { issue_w(NT); if (NT > 1) issue_w(NT + 1); }
         const float loss = d.C == 10 ? tail_eval<N1, 10>(d, sm, cnt) : tail_eval<N1, 0>(d, sm, cnt);
 
         // ---- backward: tail gradient, then g = X^T . dPre tile by tile, straight to HBM
         float gsum = 0.f;
         for (int i = tid; i < d.tailP; i += blockDim.x) {
             const float g = sm[d.off_tg + i];
-            gout[d.P1 + i] = g;
+            if (FUSED) {                                      // b1, W2, b2: same update, one parameter at a time
+                const int p = d.P1 + i;
+                const float wo = wE[p];
+                const float lr = action_to_lr(act[d.row_lex ? d.row_of_param[p] : p], d.act_ver);
+                const float wn = fmaf(-g, lr, wo);
+                wOut[p] = wn;
+                rw[p] = ratio_nn(wn, wo);
+                s_absw += fabsf(wn);
+                s_lr += (double)lr;
+                s_lr2 += (double)lr * (double)lr;
+            } else {
+                gout[d.P1 + i] = g;
+            }
             gsum += g;
         }
         const int rgi = tid >> 3, cgi = tid & 7, kl = rgi * 4;
@@ -2443,20 +2484,82 @@ __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant
                         ffma2(g2[j][3], x2, d1.y);
                     }
                 }
-                release(q);                                   // the tile is in registers now
+                if (!FUSED) release(q);                       // the tile is in registers now
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) unpack2(g2[j][c], g[j][2 * c], g[j][2 * c + 1]);
+                if (FUSED) {
+                    // rows of the agents first (the only dependent loads), all in flight at once
+                    const int pbase = (k0 + kl) * N1 + 4 * cgi;
+                    int4 r4[4][2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float *dst = gout + (size_t)(k0 + kl + j) * N1 + 4 * cgi;
-                    *reinterpret_cast<float4 *>(dst) = make_float4(g[j][0], g[j][1], g[j][2], g[j][3]);
-                    *reinterpret_cast<float4 *>(dst + half) = make_float4(g[j][4], g[j][5], g[j][6], g[j][7]);
-                    gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int p = pbase + j * N1 + hh * half;
+                            r4[j][hh] = d.row_lex ? *reinterpret_cast<const int4 *>(d.row_of_param + p)
+                                                  : make_int4(p, p + 1, p + 2, p + 3);
+                        }
+                    float av[4][8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            av[j][4 * hh + 0] = act[r4[j][hh].x]; av[j][4 * hh + 1] = act[r4[j][hh].y];
+                            av[j][4 * hh + 2] = act[r4[j][hh].z]; av[j][4 * hh + 3] = act[r4[j][hh].w];
+                        }
+                    tc::mbar_wait(&wfull[q & 1], (wph >> (q & 1)) & 1u);
+                    wph ^= 1u << (q & 1);
+                    const float *ws = W0 + (q & 1) * wstep + kl * N1 + 4 * cgi;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float4 wo4 = *reinterpret_cast<const float4 *>(ws + j * N1 + hh * half);
+                            const float wo[4] = {wo4.x, wo4.y, wo4.z, wo4.w};
+                            float wn[4], aw[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float lr = action_to_lr(av[j][4 * hh + c], d.act_ver);
+                                wn[c] = fmaf(-g[j][4 * hh + c], lr, wo[c]);
+                                aw[c] = ratio_nn(wn[c], wo[c]);          // utils_env.py:158-159
+                                s_absw += fabsf(wn[c]);
+                                s_lr += (double)lr;
+                                s_lr2 += (double)lr * (double)lr;
+                            }
+                            const int p = pbase + j * N1 + hh * half;
+                            *reinterpret_cast<float4 *>(wOut + p) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+                            *reinterpret_cast<float4 *>(rw + p) = make_float4(aw[0], aw[1], aw[2], aw[3]);
+                        }
+                    release(q);                               // the old weights have been read
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float *dst = gout + (size_t)(k0 + kl + j) * N1 + 4 * cgi;
+                        *reinterpret_cast<float4 *>(dst) = make_float4(g[j][0], g[j][1], g[j][2], g[j][3]);
+                        *reinterpret_cast<float4 *>(dst + half) = make_float4(g[j][4], g[j][5], g[j][6], g[j][7]);
+                        gsum += ((g[j][0] + g[j][1]) + (g[j][2] + g[j][3])) + ((g[j][4] + g[j][5]) + (g[j][6] + g[j][7]));
+                    }
                 }
             } else {                                          // the producer warp has no rows here
+                if (FUSED) {
+                    tc::mbar_wait(&wfull[q & 1], (wph >> (q & 1)) & 1u);
+                    wph ^= 1u << (q & 1);
+                }
                 release(q);
+            }
+        }
+        if (FUSED) {                                          // update_kernel's statistics, whole env in segment 0
+            double *red = reinterpret_cast<double *>(sm + d.off_red2);
+            const double t0 = block_sum((double)s_absw, red), t1 = block_sum(s_lr, red), t2 = block_sum(s_lr2, red);
+            if (tid == 0) {
+                double *out = d.part_u + (size_t)e * d.nsegU * 4;
+                out[0] = t0; out[1] = t1; out[2] = t2;
+                for (int seg = 1; seg < d.nsegU; ++seg) { out[seg * 4] = 0.0; out[seg * 4 + 1] = 0.0; out[seg * 4 + 2] = 0.0; }
             }
         }
         if (!SECOND) continue;
@@ -3348,6 +3451,7 @@ struct b2e_env {
     int chunk_envs, obs_grid;
     bool use_eval_kernel;            // first layer fits the streamed-operand eval kernel
     bool eval_c;                     // eval_kernel instantiated for N1 = 64, KT = 112 (config 4)
+    bool fuse_update;                // first eval applies the update itself (eval_bulk_kernel<false, true>; opt-in with B2E_FUSE_UPDATE=1)
     bool eval_bulk;                  // ... and its bulk-copy / mbarrier pipelined form (B2E_EVAL_BULK=0 disables)
     int nchunks, eval_ctas_per_sm;   // B2E_CHUNKS experiment
     bool use_thin;                   // softmax regression: thin_eval_kernel
@@ -3865,6 +3969,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
              cudaFuncSetAttribute(eval_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)h->smem_eval) != cudaSuccess))
             return bail("b2e_create: bulk eval kernel does not fit shared memory");
+        h->fuse_update = h->eval_bulk && d.env_kind == B2E_ENV_MULTIOPTLRS &&
+                         getenv("B2E_FUSE_UPDATE") && atoi(getenv("B2E_FUSE_UPDATE")) != 0 &&
+                         cudaFuncSetAttribute(eval_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)h->smem_eval) == cudaSuccess;
         h->nchunks = getenv("B2E_CHUNKS") ? atoi(getenv("B2E_CHUNKS")) : 1;
         if (h->nchunks > 1) {
             int prio_least = 0, prio_greatest = 0;
@@ -3885,6 +3993,12 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, eval_bulk_kernel<true>, 256, h->smem_eval) !=
                     cudaSuccess || occ_b < occ_ev)
                 h->eval_bulk = false;
+            if (h->fuse_update &&
+                (!h->eval_bulk || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, eval_bulk_kernel<false, true>, 256,
+                                                                                h->smem_eval) != cudaSuccess || occ_b < occ_ev))
+                h->fuse_update = false;
+        } else {
+            h->fuse_update = false;
         }
         h->eval_grid = occ_ev * h->num_sms;
         h->eval_ctas_per_sm = getenv("B2E_EVAL_CTAS") ? atoi(getenv("B2E_EVAL_CTAS")) : occ_ev;
@@ -4112,7 +4226,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
-        if (h->eval_bulk) eval_bulk_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        if (h->eval_bulk && h->fuse_update) eval_bulk_kernel<false, true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
+        else if (h->eval_bulk) eval_bulk_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
@@ -4126,7 +4241,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         h->launches--;
     }
     mark(1);
-    update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
+    if (h->fuse_update && h->eval_bulk && h->use_eval_kernel && !h->use_tc) h->launches--;   // the first eval did it
+    else update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
     if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);

@@ -468,3 +468,36 @@ def test_full_size_properties_mlp():
         assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
     for a, b in zip(outs[0], outs[1]):                 # row order only permutes rows
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_fused_update_variant_equals_the_four_kernel_pipeline(monkeypatch):
+    """B2E_FUSE_UPDATE=1 (the first eval kernel applies the update in its backward epilogue) against
+    the default pipeline on the config-4 shape: same arithmetic per parameter, so weights and
+    observations agree bit for bit; the per-env statistics are summed in another order."""
+    import torch
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    rng = np.random.RandomState(11)
+    feats = rng.uniform(size=(256, 784)).astype(np.float32)
+    labels = rng.randint(0, 10, 256).astype(np.int32)
+    runs = []
+    for fused in (False, True):
+        if fused:
+            monkeypatch.setenv('B2E_FUSE_UPDATE', '1')
+        else:
+            monkeypatch.delenv('B2E_FUSE_UPDATE', raising=False)
+        env = BatchedOptEnv(ProblemSpec('softmax', 784, (64,), 10), feats, labels, 5, batch_size=32,
+                            max_batches=6, seeds=list(range(5)), init_seed=9)
+        env.reset()
+        act_rng = np.random.RandomState(4)
+        launches, trail = env.launch_count, []
+        for _ in range(8):                                   # crosses an auto-reset (max_batches=6)
+            actions = torch.as_tensor(act_rng.uniform(0, 3, env.num_rows).astype(np.float32), device=env.device)
+            obs, reward, done, info = env.step(actions)
+            trail.append((obs.cpu().numpy().copy(), reward.cpu().numpy().copy(), done.cpu().numpy().copy(),
+                          info.cpu().numpy().copy()))
+        runs.append((trail, env.launch_count - launches))
+        env.close()
+    assert runs[1][1] < runs[0][1]                           # one launch fewer per step
+    for (obs_a, rew_a, done_a, info_a), (obs_b, rew_b, done_b, info_b) in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(obs_a, obs_b) and np.array_equal(rew_a, rew_b) and np.array_equal(done_a, done_b)
+        assert np.allclose(info_a, info_b, rtol=1e-6, atol=1e-9, equal_nan=True)
