@@ -2331,9 +2331,10 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
 // a second time into the W stage that idles during the backward pass (an L2 hit mostly: this CTA
 // read it a few microseconds ago), so g0 is never written, and w / g0 are not re-read from HBM by a
 // separate kernel.  Saves 3 of the step's 35 words per parameter and one launch -- but no time:
-// measured 1.54 ms against 0.84 + 0.70 ms for the two kernels (profiles/r1_notes.md): the epilogue
-// issues about as many instructions per tile as the FMA loop, and the eval kernel is issue bound,
-// while the separate update kernel runs at 90 % of the HBM rate.  Opt-in (B2E_FUSE_UPDATE=1).
+// measured 1.54 ms against 0.84 + 0.70 ms for the two kernels (profiles/r1_notes.md): the epilogue's
+// dependent chain (row lookup -> action gather -> arithmetic -> stores) is appended to each CTA's
+// timeline with nothing running underneath it, while the separate update kernel streams at 90 % of
+// the HBM rate.  Opt-in (B2E_FUSE_UPDATE=1).
 template <bool SECOND, bool FUSED = false>
 __global__ void __launch_bounds__(256, 2) eval_bulk_kernel(const __grid_constant__ Dev d,
                                                            const __grid_constant__ StepArgs a) {
