@@ -285,3 +285,47 @@ def test_device_rollout_matches_a_manual_loop():
     assert results[0][1] == results[1][1] == 8            # every env ended once (max_batches=6)
     assert np.allclose(results[0][0], results[1][0], rtol=1e-6)
     assert np.allclose(results[0][2], results[1][2], rtol=1e-5, atol=1e-6)
+
+
+def test_device_episode_monitor_in_a_device_rollout(tmp_path):
+    """Episode bookkeeping on the device next to a host replay of the same steps: reward sums,
+    lengths (max_batches), the terminal `loss` info and the CSV the reference's tools read."""
+    import pandas as pd
+    import torch
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy, device_rollout
+    from custom_envs_b200.wrappers.device_monitor import DeviceEpisodeMonitor
+    rng = np.random.RandomState(0)
+    feats = rng.uniform(size=(150, 4)).astype(np.float32)
+    labels = (np.arange(150) % 3).astype(np.int32)
+    env = BatchedOptEnv(ProblemSpec('softmax', 4, (), 3), feats, labels, 16, batch_size=32,
+                        max_batches=5, seeds=list(range(16)), init_seed=2)
+    env.reset()
+    torch.manual_seed(1)
+    policy = SharedMlpPolicy(env.obs_dim).to(env.device)
+    monitor = DeviceEpisodeMonitor(env.num_envs, str(tmp_path / 'run'), info_keywords=('loss', 'batch_loss'),
+                                   device=env.device)
+    seen = []
+
+    def hook(t, obs, reward, done, info):
+        monitor.on_step(t, obs, reward, done, info)
+        seen.append((reward.cpu().numpy().copy(), done.cpu().numpy().copy(), info.cpu().numpy().copy()))
+
+    device_rollout(env, policy.act, 12, on_step=hook)
+    rows = monitor.close()
+    env.close()
+    assert len(rows) == 16 * 2                           # every env ends at step 5 and 10 (or earlier if it diverges)
+    total = np.zeros(16)
+    want = {}
+    episode = np.ones(16, int)
+    for reward, done, info in seen:
+        total += reward
+        for e in np.nonzero(done)[0]:
+            want[(e, episode[e])] = (total[e], int(info[e, 15]), info[e, 0])
+            total[e], episode[e] = 0.0, episode[e] + 1
+    for row in rows:
+        ret, length, loss = want[(row['env'], row['episode'])]
+        assert abs(row['r'] - ret) < 1e-4 and row['l'] == length and abs(row['loss'] - loss) < 1e-9
+    frame = pd.read_csv(tmp_path / 'run.mon.csv')
+    assert list(frame.columns) == sorted(['env', 'r', 'l', 'current_reward', 'episode', 't', 'loss', 'batch_loss'])
+    assert len(frame) == len(rows)

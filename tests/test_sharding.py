@@ -76,3 +76,95 @@ def test_numa_binding_reads_the_gpu_node_from_sysfs(tmp_path):
     assert bind_to_gpu_numa('0000:1b:00.0', str(tmp_path)) == -1
     assert bind_to_gpu_numa('0000:ff:00.0', str(tmp_path)) == -1          # unknown device
     assert sorted(os.sched_getaffinity(0)) == allowed
+
+
+def _host_episode_table(steps, first_env):
+    """What the reference's per-env Monitor would log (utils_logging.py:96-113): reward sum,
+    length, last reward, episode counter per finished episode."""
+    rows, total, episode = [], {}, {}
+    for reward, done, info in steps:
+        for e in range(len(reward)):
+            total[e] = total.get(e, 0.0) + float(reward[e])
+            if done[e]:
+                rows.append(dict(env=first_env + e, r=round(total[e], 6), l=int(info[e, 15]),
+                                 current_reward=float(reward[e]), episode=episode.get(e, 1),
+                                 batch_loss=float(info[e, 1])))
+                total[e] = 0.0
+                episode[e] = episode.get(e, 1) + 1
+    return rows
+
+
+def _fake_steps(num_envs, count, seed):
+    rng = np.random.RandomState(seed)
+    length = np.zeros(num_envs)
+    steps = []
+    for _ in range(count):
+        length += 1
+        reward = rng.normal(size=num_envs).astype(np.float32)
+        done = rng.uniform(size=num_envs) < 0.3
+        info = np.zeros((num_envs, 16))
+        info[:, 15], info[:, 1] = length, rng.uniform(size=num_envs)
+        steps.append((reward, done.astype(np.uint8), info))
+        length[done] = 0
+    return steps
+
+
+def test_device_episode_monitor_matches_per_env_monitors(tmp_path):
+    import pandas as pd
+    from custom_envs_b200.wrappers.device_monitor import DeviceEpisodeMonitor
+    steps = _fake_steps(6, 25, seed=1)
+    monitor = DeviceEpisodeMonitor(6, str(tmp_path / 'job'), info_keywords=('batch_loss',), first_env=12,
+                                   device='cpu', capacity=64)
+    split = DeviceEpisodeMonitor(6, str(tmp_path / 'monitor'), first_env=0, device='cpu', capacity=64,
+                                 split_by_env=True)
+    got = []
+    for t, (reward, done, info) in enumerate(steps):
+        args = (t, None, torch.from_numpy(reward), torch.from_numpy(done), torch.from_numpy(info))
+        monitor.on_step(*args)
+        split.on_step(*args)
+        if t % 10 == 9:
+            got += monitor.flush()                       # flushes in the middle keep the running sums
+    got += monitor.close()
+    split.close()
+    want = _host_episode_table(steps, 12)
+    assert len(got) == len(want) > 20
+    key = lambda row: (row['env'], row['episode'])       # noqa: E731
+    for a, b in zip(sorted(got, key=key), sorted(want, key=key)):
+        assert all(a[name] == b[name] for name in ('env', 'l', 'episode', 'current_reward', 'batch_loss'))
+        assert abs(a['r'] - b['r']) < 1e-5
+    frame = pd.read_csv(tmp_path / 'job.mon.csv')
+    assert list(frame.columns) == sorted(frame.columns) and len(frame) == len(want)       # utils_logging.py:64
+    files = sorted(tmp_path.glob('monitor_*.mon.csv'))                                     # compile_exp.py:15-16
+    assert len(files) == 6 and 'env' not in pd.read_csv(files[0]).columns
+    assert sum(len(pd.read_csv(name)) for name in files) == len(want)
+    small = DeviceEpisodeMonitor(6, None, device='cpu', capacity=2)
+    for t, (reward, done, info) in enumerate(steps):
+        small.on_step(t, None, torch.from_numpy(reward), torch.from_numpy(done), torch.from_numpy(info))
+    with pytest.raises(RuntimeError):
+        small.flush()                                    # dropped episodes are an error, not silence
+
+
+def _monitor_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from custom_envs_b200.wrappers.device_monitor import DeviceEpisodeMonitor
+    first, count = shard_range(7, world, rank)
+    monitor = DeviceEpisodeMonitor(count, os.path.join(out_dir, 'job'), first_env=first, device='cpu', capacity=64)
+    for t, (reward, done, info) in enumerate(_fake_steps(count, 12, seed=10 + rank)):
+        monitor.on_step(t, None, torch.from_numpy(reward), torch.from_numpy(done), torch.from_numpy(info))
+    rows = monitor.close()
+    np.save(os.path.join(out_dir, 'rows%d.npy' % rank), np.array([[r['env'], r['l'], r['episode']] for r in rows]))
+    dist.destroy_process_group()
+
+
+def test_device_episode_monitor_gathers_shards_gloo_world2(tmp_path):
+    import pandas as pd
+    mp.spawn(_monitor_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    want = []
+    for rank in range(2):
+        first, count = shard_range(7, 2, rank)
+        want += [[r['env'], r['l'], r['episode']] for r in _host_episode_table(_fake_steps(count, 12, seed=10 + rank), first)]
+    for rank in range(2):                                # every rank sees the whole job's episodes
+        assert np.load(tmp_path / ('rows%d.npy' % rank)).tolist() == want
+    frame = pd.read_csv(tmp_path / 'job.mon.csv')       # written once, by rank 0
+    assert frame[['env', 'l', 'episode']].values.tolist() == want
