@@ -329,3 +329,27 @@ def test_device_episode_monitor_in_a_device_rollout(tmp_path):
     frame = pd.read_csv(tmp_path / 'run.mon.csv')
     assert list(frame.columns) == sorted(['env', 'r', 'l', 'current_reward', 'episode', 't', 'loss', 'batch_loss'])
     assert len(frame) == len(rows)
+
+
+def test_integration_training_loop_snippet(tmp_path):
+    """INTEGRATION.md section 5 at a small env count: device data set -> env -> policy rollout ->
+    episode monitor, nothing on the host until the flush."""
+    import warnings
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    from custom_envs_b200.data import load_data
+    from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy, device_rollout
+    from custom_envs_b200.wrappers.device_monitor import DeviceEpisodeMonitor
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        data = load_data('mnist-test', batch_size=32, device='cuda:0')       # synthetic bytes offline
+    assert tuple(data.features.shape) == (10000, 49) and data.num_classes == 10
+    env = BatchedOptEnv(ProblemSpec('softmax', 49, (64,), data.num_classes), data.features, data.targets,
+                        num_envs=64, batch_size=32, max_batches=6, max_history=5)
+    env.reset()
+    policy = SharedMlpPolicy(env.obs_dim).to('cuda:0')
+    monitor = DeviceEpisodeMonitor(env.num_envs, str(tmp_path / 'monitor'), info_keywords=('loss', 'actions_mean'))
+    returns, finished = device_rollout(env, policy.act, steps=13, on_step=monitor.on_step)
+    rows = monitor.flush()
+    env.close()
+    assert finished == len(rows) >= 2 * 64 and all(row['l'] <= 6 for row in rows)
+    assert (tmp_path / 'monitor.mon.csv').is_file()
