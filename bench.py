@@ -191,6 +191,8 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
+        # stdout carries the one JSON line: NCCL's version banner / debug lines go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=device)
     numa_node = -1
     if os.environ.get('B2E_NUMA_BIND', '1') != '0':
