@@ -22,6 +22,7 @@ Reported on one JSON line:
             bounded sample of the same workload
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -47,6 +48,21 @@ def synthetic_data(rows=ROWS):
     feats = ((feats - lo) / (hi - lo + 1e-8)).astype(np.float32)      # utils_math.normalize
     labels = rng.randint(0, C, size=rows).astype(np.int32)
     return feats, labels
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """File descriptor 1 points at stderr inside the block, so that lines native libraries write to
+    stdout do not end up next to the one JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 def measured_peaks():
@@ -191,9 +207,9 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's version banner / debug lines go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=device)
+        with stdout_to_stderr():              # NCCL prints its version banner when the communicator is made
+            dist.init_process_group('nccl', device_id=device)
+            dist.barrier()
     numa_node = -1
     if os.environ.get('B2E_NUMA_BIND', '1') != '0':
         # one process per GPU: run on (and first-touch the pinned staging buffers of the e2e
