@@ -6,7 +6,6 @@ Two flavours exist in the reference and both are kept: the strict one
 stepping a finished env raises) and the lenient callback one the training scripts use
 (utils/utils_logging.py:15-156)."""
 import time
-from collections import defaultdict
 from pathlib import Path
 
 import pandas as pd

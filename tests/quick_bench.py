@@ -1,5 +1,5 @@
 """Ad-hoc timing probe (not a test): ms/step of the fused kernel at the BASELINE shapes."""
-import sys, time
+import sys
 import numpy as np
 import torch
 sys.path.insert(0, '.')

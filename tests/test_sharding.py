@@ -168,3 +168,26 @@ def test_device_episode_monitor_gathers_shards_gloo_world2(tmp_path):
         assert np.load(tmp_path / ('rows%d.npy' % rank)).tolist() == want
     frame = pd.read_csv(tmp_path / 'job.mon.csv')       # written once, by rank 0
     assert frame[['env', 'l', 'episode']].values.tolist() == want
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone times
+    the oracle port and prints ONE JSON line with the contract's keys; the other rank exits 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), os.path.join(root, 'bench.py'),
+           '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '1']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference' and line['n_gpus'] == 2 and line['unit'] == 'env-steps/s'
+    assert line['value'] > 0 and line['higher_is_better'] is True and line['vs_baseline'] is None
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0,
+                           'd2h_bytes_per_step': 0}
+    assert line['config']['workload'].startswith('MultiOptLRs MLP 784-64-10')
