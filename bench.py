@@ -333,7 +333,8 @@ def gpu_arm(args):
         achieved = dominant['gbs'] if dominant else step_gbs
         cores = os.cpu_count() or 1
         threads = min(cores, 32)
-        cpu_value, cpu_elapsed = cpu_env_steps_per_s(8, threads, 20, 1)
+        cpu_steps = 30                          # ~12 s of host work on the pool's 16-32 core boxes
+        cpu_value, cpu_elapsed = cpu_env_steps_per_s(8, threads, cpu_steps, 1)
         line = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
@@ -362,8 +363,8 @@ def gpu_arm(args):
                                         'bytes_per_step': BYTES_PER_ENV_STEP * envs,
                                         'note': 'SURVEY 8d algorithmic bytes of the fused step / step time'}},
             'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d envs x 20 steps of the workload (oracle numpy float32, '
-                                       '%d threads), %.1f s' % (8 * threads, threads, cpu_elapsed)},
+                             'sample': '%d envs x %d steps of the workload (oracle numpy float32, '
+                                       '%d threads), %.1f s' % (8 * threads, cpu_steps, threads, cpu_elapsed)},
         }
         print(json.dumps(line), flush=True)
     env.close()
