@@ -290,3 +290,44 @@ def test_headers_are_plain_c_and_a_c_client_resolves_every_entry_point(tmp_path)
                     os.path.join(here, 'c_abi_smoke.c'), '-o', exe, '-ldl'], check=True)
     out = subprocess.run([exe, _lib.LIB_PATH], check=True, capture_output=True, text=True)
     assert 'c abi ok' in out.stdout
+
+
+def test_device_dataset_container_follows_the_batching_rules():
+    """DeviceDataSet (what load_data(..., device=) returns) on CPU tensors: ceil(N/B) batches, ragged
+    last batch, class count inferred from the label ranks (dataset/inmemorydataset.py:11-28)."""
+    import torch
+    from custom_envs_b200.dataset import DeviceDataSet
+    feats, ranks = torch.arange(150 * 4, dtype=torch.float32).reshape(150, 4), torch.arange(150, dtype=torch.int32) % 3
+    data = DeviceDataSet(feats, ranks, batch_size=32)
+    assert len(data) == 5 and data.num_classes == 3 and data.on_device
+    assert data.feature_shape == (4,) and data.target_shape == (3,)
+    assert [len(batch.features) for batch in data] == [32, 32, 32, 32, 22]
+    assert torch.equal(data[4].labels, ranks[128:])
+    assert len(DeviceDataSet(feats, ranks)) == 1                      # batch_size=None: the whole set
+    with pytest.raises(AssertionError):
+        DeviceDataSet(feats, ranks[:10])
+
+
+def test_policy_actions_chunks_and_clips():
+    """The chunked policy evaluation of device_rollout on CPU tensors: every row is visited once
+    whatever the chunk size, actions are clipped to MultiOptLRs' Box [-4, 6]."""
+    import torch
+    from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy, policy_actions
+    obs = torch.linspace(-30, 30, 101 * 15).reshape(101, 15)
+    calls = []
+
+    def act(chunk):
+        calls.append(len(chunk))
+        return chunk.sum(dim=1)
+
+    want = obs.sum(dim=1).clamp(-4.0, 6.0)
+    for chunk in (1, 7, 101, 1000):
+        calls.clear()
+        out = policy_actions(act, obs, torch.empty(101), row_chunk=chunk)
+        assert torch.equal(out, want) and sum(calls) == 101 and max(calls) <= chunk
+    torch.manual_seed(0)
+    policy = SharedMlpPolicy(15)
+    mean, value = policy(obs)
+    assert mean.shape == value.shape == (101,)
+    gen = torch.Generator().manual_seed(1)
+    assert policy.act(obs, generator=gen).shape == (101,)
