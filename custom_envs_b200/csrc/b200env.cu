@@ -26,196 +26,10 @@
 
 #include "b200env.h"
 
+#include "b200env_shared.cuh"
+#include "b200tc.h"
+
 namespace {
-
-constexpr int RAW_DEPTH = 5;      // reference envs/multioptlrs.py:42
-constexpr int MAXI = 4;           // forward work items per warp
-constexpr int NSTAT = 8;
-
-enum { MODE_STEP = 0, MODE_RESET = 1, MODE_EVAL = 2, MODE_EVAL_STEP = 3, MODE_EVAL_FIRST = 4 };
-enum { PASS_U = 0, PASS_G = 1, PASS_R = 2, PASS_E = 3, PASS_S = 4 };
-enum { ST_ABSW = 0, ST_LR = 1, ST_LR2 = 2, ST_G = 3, ST_ABSADJG = 4, ST_GDIFF = 5, ST_STATE = 6 };
-
-struct EnvScalars {
-    double raw_gsum[RAW_DEPTH];
-    float raw_loss[RAW_DEPTH];
-    float adj_loss[B2E_MAX_HISTORY];
-    float loss_prev;
-    int raw_pos, head, nvalid, step, cursor, ord_sel, episode;
-};
-
-struct Dev {
-    int env_kind, kind, hidden;
-    int D, Dp, Ds, N1, N1p, C, Cp;
-    int P, Pp, P1, tailP, N, B, E, H, OD;
-    int max_batches, act_ver, rew_ver, obs_ver;
-    int KT, ntiles;
-    int nsc, ncc, nks, fitems;
-    int N1g, KR, gcc;
-    int row_lex, index_mode, auto_reset;
-    unsigned long long seed;
-    float lim1, lim2;
-    const float *X;
-    const int *labels;
-    const float *targets;
-    float *w, *gprev, *gnext, *ringw, *ringg;
-    double *part;
-    EnvScalars *sc;
-    int *ord;
-    const int *perm;
-    long long perm_stride;
-    const int *row_of_param;
-    const int *param_of_row;
-    int off_red2;
-    int off_T, off_T2, off_H, off_dP, off_tw, off_tg, off_Z, off_red, off_stage, off_rows, off_idx,
-        off_y, off_lb, off_misc;
-    int stage_stride, xslack;
-    int split, nseg;
-    int fast, cg;                    // register-tiled GEMM path (N1 % 8 == 0, B <= 32, 256 threads)
-    int ev_X0, ev_X1, ev_W0, ev_W1, ev_XS;   // eval kernel: streamed X / W tile buffers
-    int nsegU;
-    double *part_u;
-    // observation layout (utils/utils_env.py:22-44): first column of each key's block or -1
-    int col_w, col_l, col_g;
-    float *w2, *g2;                  // x_{t-2} planes of the raw History, observation version 2
-    // generic dense stack (any number of hidden layers / batch size): see gen_eval_kernel
-    int generic, nlayers;            // nlayers = Dense layers = hidden layers + 1
-    int dims[B2E_MAX_LAYERS + 1];    // widths n_0 = D, n_1.., n_nlayers = C
-    int woff[B2E_MAX_LAYERS], boff[B2E_MAX_LAYERS];   // parameter offsets of kernel / bias of layer l
-    int aoff[B2E_MAX_LAYERS + 1];    // workspace offset of the activations of layer l (0 = inputs)
-    int doff0, doff1;                // two delta buffers [B, max width]
-    float *ws;                       // per-CTA workspace
-    long long ws_stride;
-};
-
-struct StepArgs {
-    const float *actions;
-    const int *ext_idx;
-    const int *ext_cnt;
-    float *obs;
-    float *reward;
-    unsigned char *done;
-    double *info;
-    const unsigned char *mask;
-    const float *init_params;
-    float *grad_out;
-    float *loss_out;
-    int mode;
-    int e_begin, e_count;
-};
-
-struct Stats {
-    float f[NSTAT];
-    double lr, lr2;
-};
-
-// ------------------------------------------------------------------ small helpers
-__device__ __forceinline__ float nan_to_num_f(float x) {
-    if (x != x) return 0.0f;
-    if (isinf(x)) return copysignf(FLT_MAX, x);
-    return x;
-}
-__device__ __forceinline__ double nan_to_num_d(double x) {
-    if (x != x) return 0.0;
-    if (isinf(x)) return copysign(DBL_MAX, x);
-    return x;
-}
-__device__ __forceinline__ float clip_m1(float x) {          // multioptlrs.py:99
-    return fminf(fmaxf(nan_to_num_f(x), -100.0f), 100.0f) - 1.0f;
-}
-__device__ __forceinline__ float action_to_lr(float a, int ver) {   // utils_env.py:102-123
-    switch (ver) {
-        case 0: return exp10f(a - 4.0f);
-        case 1: return a * 1e-3f;
-        case 2: return exp2f(a);
-        default: return fmaxf((a + 1e3f) * 1e-6f, 0.0f);
-    }
-}
-__device__ __forceinline__ float action_to_delta(float a, int ver) {  // multioptimize.py:95-102
-    if (ver == 1) return a * 1e-3f;
-    const float mag = exp10f(fabsf(a) - 3.0f);
-    return a > 0.f ? mag : (a < 0.f ? -mag : 0.f);
-}
-// adjusted weight / gradient / loss per observation version (utils/utils_env.py:126-164);
-// x0 newest, x1, x2 the two entries before it in the raw History
-__device__ __forceinline__ float adjust_w(int ver, float w0, float w1, float w2) {
-    switch (ver) {
-        case 2: return fabsf(w1 - w2) / (fabsf(w0 - w1) + 1e-8f);
-        case 3: return nan_to_num_f(w0 / fabsf(w1));
-        default: return w0 / (fabsf(w1) + 1e-3f);
-    }
-}
-__device__ __forceinline__ float adjust_g(int ver, float g0, float g1, float g2) {
-    switch (ver) {
-        case 1: return g0 * 1e2f;
-        case 2: return (g0 - g1) / (fabsf(g1 - g2) + 1e-3f);
-        case 3: return nan_to_num_f(g0 / fabsf(g1));
-        default: return g0 / (fabsf(g1) + 1e-3f);
-    }
-}
-__device__ __forceinline__ double adjust_l(int ver, double l0, double l1, double l2) {
-    switch (ver) {
-        case 2: return (l0 - l1) / (fabs(l1 - l2) + 1e-3);
-        case 3: return nan_to_num_d(l0 / fabs(l1));
-        default: return l0 / (fabs(l1) + 1e-3);
-    }
-}
-__device__ __forceinline__ float glorot(unsigned long long seed, int e, int episode, int p,
-                                        float limit) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(p + 1);
-    z ^= ((unsigned long long)(unsigned)e << 32) | (unsigned)episode;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    float u = (float)((unsigned)(z >> 40)) * (1.0f / 16777216.0f);
-    return (2.0f * u - 1.0f) * limit;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-struct Totals {
-    double v[NSTAT];
-};
-
-__device__ __forceinline__ void zero_stats(Stats &st) {
-#pragma unroll
-    for (int i = 0; i < NSTAT; ++i) st.f[i] = 0.f;
-    st.lr = st.lr2 = 0.0;
-}
-
-// deterministic block reduction of the per-thread statistics; result valid in thread 0
-__device__ void block_reduce(const Stats &st, Totals &tot, double *red) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NSTAT; ++i) {
-        double v = (i == ST_LR) ? st.lr : (i == ST_LR2) ? st.lr2 : (double)st.f[i];
-        v = warp_sum(v);
-        if (lane == 0) red[warp * NSTAT + i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAT; ++i) {
-            double v = 0.0;
-            for (int w = 0; w < nw; ++w) v += red[w * NSTAT + i];
-            tot.v[i] = v;
-        }
-    }
-    __syncthreads();
-}
-
-// deterministic block sum of one value (fixed order); result in every thread
-__device__ double block_sum(double v, double *red) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += red[w];
-    return t;
-}
 
 // ---------------------------------------------------------------- minibatch gather
 __device__ void load_batch(const Dev &d, float *sm, const int *idx_g, int cnt) {
@@ -727,7 +541,7 @@ struct EpiCtx {
 constexpr int SPAN_CAP = 160;        // rows a warp's 128-parameter chunk may span when staged by row
 
 __device__ __forceinline__ float ratio_nn(float num, float den) {    // nan_to_num(num / |den|)
-    return nan_to_num_f(__fdividef(num, fabsf(den)));
+    return nan_to_num_f(num / fabsf(den));       // IEEE division: huge / denormal denominators behave as in numpy
 }
 __device__ __forceinline__ float clip_only_m1(float x) {             // x already nan_to_num'ed
     return fminf(fmaxf(x, -100.0f), 100.0f) - 1.0f;
@@ -1008,35 +822,6 @@ __device__ void epilogue(const Dev &d, const StepArgs &a, float *sm, const EpiCt
     }
 }
 
-// ------------------------------------------------------------- minibatch stream
-__device__ __forceinline__ const int *order_ptr(const Dev &d, int e, int sel) {
-    return d.ord + ((size_t)sel * d.E + e) * d.N;
-}
-
-// InMemoryDataSet.on_epoch_end with the env's fixed permutation: new[i] = old[perm[i]]
-__device__ void shuffle_order(const Dev &d, int e, EnvScalars *sc) {
-    const int sel = sc->ord_sel;
-    const int *src = order_ptr(d, e, sel);
-    int *dst = d.ord + ((size_t)(sel ^ 1) * d.E + e) * d.N;
-    const int *pm = d.perm + (size_t)e * d.perm_stride;
-    for (int i = threadIdx.x; i < d.N; i += blockDim.x) dst[i] = src[pm[i]];
-    __syncthreads();
-    if (threadIdx.x == 0) sc->ord_sel = sel ^ 1;
-    __syncthreads();
-}
-
-__device__ void current_batch(const Dev &d, const StepArgs &a, int e, const EnvScalars *sc,
-                              const int *&idx, int &cnt) {
-    if (d.kind == B2E_PROBLEM_FUNC) { idx = nullptr; cnt = 0; return; }
-    if (d.index_mode == B2E_INDEX_EXTERNAL) {
-        idx = a.ext_idx + (size_t)e * d.B;
-        cnt = a.ext_cnt[e];
-    } else {
-        const int lo = sc->cursor * d.B;
-        idx = order_ptr(d, e, sc->ord_sel) + lo;
-        cnt = min(d.B, d.N - lo);
-    }
-}
 
 __device__ void load_tail(const Dev &d, float *sm, const float *wE) {
     float *tw = sm + d.off_tw;
@@ -1301,68 +1086,6 @@ __device__ void step_env(const Dev &d, const StepArgs &a, float *sm, int e) {
     if (done && d.auto_reset && !d.split) reset_env<BIG>(d, a, sm, e);
 }
 
-// Scalar bookkeeping of one env-step once g_t and L_t are known (one thread): raw and
-// adjusted loss histories, reward, done, the scalar info entries, minibatch cursor.
-// misc[4] = 1 when the epoch wrapped (the CTA reshuffles), misc[1] = done.
-__device__ void step_scalars(const Dev &d, const StepArgs &a, EnvScalars *sc, int e, float loss,
-                             double gsum, float *misc) {
-    const bool lrs = d.env_kind == B2E_ENV_MULTIOPTLRS;
-    const int head_new = (sc->head + 1) % d.H;
-    const int nvalid_new = min(sc->nvalid + 1, d.H);
-    const double l1 = (double)sc->raw_loss[sc->raw_pos];
-    const double l2 = (double)sc->raw_loss[(sc->raw_pos + RAW_DEPTH - 1) % RAW_DEPTH];
-    const double adjl = lrs ? nan_to_num_d((double)loss / fabs((double)sc->loss_prev))
-                            : adjust_l(d.obs_ver, (double)loss, l1, l2);
-    double reward;
-    switch (d.rew_ver) {                                       // utils_env.py:71-99
-        case 0: reward = -adjl; break;
-        case 1: reward = (double)(1.0f / loss); break;
-        case 2: reward = -adjl * 100.0; break;
-        case 3: reward = (double)(1.0f / loss) * 100.0; break;
-        case 4: reward = (double)logf(1.0f / loss); break;
-        case 5: reward = -(adjl - 1.0) * (adjl - 1.0); break;
-        default: reward = -(adjl - 1.0); break;
-    }
-    const int step = sc->step + 1;                             // baseenvironment.py:37
-    bool done = step >= d.max_batches;
-    if (lrs) {
-        reward = fmin(fmax(reward, -100.0), 100.0);            // multioptlrs.py:103
-        if (!done && loss > 1e4f) {                            // multioptlrs.py:105-107
-            done = true;
-            reward -= (double)(d.max_batches - step);
-        }
-    }
-    const int rp = (sc->raw_pos + 1) % RAW_DEPTH;
-    sc->raw_pos = rp;
-    sc->raw_loss[rp] = loss;
-    sc->raw_gsum[rp] = gsum;
-    sc->loss_prev = loss;
-    sc->adj_loss[head_new] = (float)adjl;
-    sc->head = head_new;
-    sc->nvalid = nvalid_new;
-    sc->step = step;
-    double gs = 0.0, ls = 0.0;
-    for (int i = 0; i < RAW_DEPTH; ++i) { gs += sc->raw_gsum[i]; ls += (double)sc->raw_loss[i]; }
-    double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
-    info[0] = done ? (double)loss : nan("");                   // multioptlrs.py:108-110
-    info[1] = (double)loss;
-    info[8] = gs / (RAW_DEPTH * (double)d.P);
-    info[9] = gs;
-    info[10] = ls / RAW_DEPTH;
-    info[11] = adjl;
-    info[14] = reward;                                         // baseenvironment.py:40
-    info[15] = (double)step;
-    a.reward[e] = (float)reward;
-    a.done[e] = done ? 1 : 0;
-    misc[1] = done ? 1.f : 0.f;
-    misc[4] = 0.f;
-    // MultiOptLRs moves to the next minibatch (multioptlrs.py:128); MultiOptimize never does
-    if (lrs && d.kind != B2E_PROBLEM_FUNC && d.index_mode == B2E_INDEX_INTERNAL) {
-        const int cur = sc->cursor + 1;                        // optimize_nn.py:102-112
-        misc[4] = (cur * d.B >= d.N) ? 1.f : 0.f;
-        sc->cursor = (cur * d.B >= d.N) ? 0 : cur;
-    }
-}
 
 // pipeline stage "evaluate at w_t" for problems the eval kernel does not cover: g_t to HBM,
 // then the step's scalars
@@ -3462,6 +3185,10 @@ struct b2e_env {
     Dev d_tc;                        // Dev with the tensor-core kernel's shared-memory layout
     size_t smem_tc;
     int tc_grid;
+    bool use_tc2;                    // warp-specialised tcgen05 eval kernel (b200tc.cu)
+    int tc2_grid;
+    int *tc2_dbg;                    // watchdog word of that kernel (device memory)
+    bool tc2_check;                  // B2E_TC_CHECK=1: synchronise and test the watchdog after every step
     float *w2, *g2, *ws;
     int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
     size_t smem_obs2;
@@ -3496,6 +3223,17 @@ int fail(b2e_handle h, const std::string &msg) {
     } while (0)
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Every entry point runs on the handle's device whatever the caller's current device is, and
+// leaves the caller's device selected afterwards.
+struct DeviceGuard {
+    int prev;
+    bool switched;
+    explicit DeviceGuard(int device) : prev(-1), switched(false) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -3849,11 +3587,15 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     for (auto &ev : h->tr) ev = nullptr;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
+    h->use_tc2 = false; h->tc2_grid = 0; h->tc2_dbg = nullptr; h->tc2_check = false;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
-    if (cudaSetDevice(cfg->device) != cudaSuccess) return bail("b2e_create: cudaSetDevice failed");
+    int dev_count = 0;
+    if (cudaGetDeviceCount(&dev_count) != cudaSuccess || cfg->device < 0 || cfg->device >= dev_count)
+        return bail("b2e_create: no such CUDA device");
+    DeviceGuard guard(cfg->device);
     if (configure(h)) return bail(h->error);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail("cudaGetDeviceProperties failed");
@@ -3950,6 +3692,19 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (occ_tc > 512 / tc::TMEM_COLS) occ_tc = 512 / tc::TMEM_COLS;    // TMEM: 512 columns per SM
         h->tc_grid = occ_tc * h->num_sms;
     }
+    {   // tcgen05 eval kernel, warp-specialised (B2E_TC=2)
+        const char *tcv = getenv("B2E_TC");
+        h->use_tc2 = h->use_eval_kernel && tcv && atoi(tcv) == 2 && b2e_tc2_supported(&h->d);
+        if (h->use_tc2) {
+            const char *err = b2e_tc2_prepare();
+            if (err) return bail(std::string("b2e_create: ") + err);
+            if (cudaMalloc((void **)&h->tc2_dbg, 64) != cudaSuccess || cudaMemset(h->tc2_dbg, 0, 64) != cudaSuccess)
+                return bail("b2e_create: cudaMalloc of the watchdog word failed");
+            h->tc2_grid = cfg->num_envs < h->num_sms ? cfg->num_envs : h->num_sms;
+            h->tc2_check = getenv("B2E_TC_CHECK") && atoi(getenv("B2E_TC_CHECK")) != 0;
+            h->use_tc = false;
+        }
+    }
     if (h->use_eval_kernel) {
         if (cudaFuncSetAttribute(eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_eval) != cudaSuccess ||
@@ -3970,7 +3725,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
              cudaFuncSetAttribute(eval_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)h->smem_eval) != cudaSuccess))
             return bail("b2e_create: bulk eval kernel does not fit shared memory");
-        h->fuse_update = h->eval_bulk && d.env_kind == B2E_ENV_MULTIOPTLRS &&
+        h->fuse_update = h->eval_bulk && !h->use_tc2 && d.env_kind == B2E_ENV_MULTIOPTLRS &&
                          getenv("B2E_FUSE_UPDATE") && atoi(getenv("B2E_FUSE_UPDATE")) != 0 &&
                          cudaFuncSetAttribute(eval_bulk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)h->smem_eval) == cudaSuccess;
@@ -4051,9 +3806,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
 
 void b2e_destroy(b2e_handle h) {
     if (!h) return;
+    DeviceGuard guard(h->cfg.device);
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
-    cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws);
+    cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws); cudaFree(h->tc2_dbg);
     cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
@@ -4066,6 +3822,7 @@ void b2e_destroy(b2e_handle h) {
 
 int b2e_bind_dataset(b2e_handle h, const float *features, const void *targets, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     Dev &d = h->d;
     if (d.kind == B2E_PROBLEM_FUNC) return fail(h, "b2e_bind_dataset: the func problem has no data");
     if (!features || !targets) return fail(h, "b2e_bind_dataset: null pointer");
@@ -4084,6 +3841,7 @@ int b2e_bind_dataset(b2e_handle h, const float *features, const void *targets, v
 int b2e_set_index_stream(b2e_handle h, const int32_t *perms, int per_env,
                          const int32_t *init_orders, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     Dev &d = h->d;
     if (d.kind == B2E_PROBLEM_FUNC || d.index_mode != B2E_INDEX_INTERNAL)
         return fail(h, "b2e_set_index_stream: handle has no internal index stream");
@@ -4114,6 +3872,7 @@ static int check_ready(b2e_handle h, const int32_t *idx, const int32_t *cnt) {
 int b2e_reset(b2e_handle h, const uint8_t *env_mask, const float *init_params,
               const int32_t *batch_idx, const int32_t *batch_cnt, float *obs_out, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (check_ready(h, batch_idx, batch_cnt)) return 1;
     StepArgs a;
     memset(&a, 0, sizeof(a));
@@ -4126,6 +3885,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
              const int32_t *batch_cnt, float *obs_out, float *reward_out, uint8_t *done_out,
              double *info_out, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (!actions || !obs_out || !reward_out || !done_out || !info_out)
         return fail(h, "b2e_step: null pointer");
     if (check_ready(h, batch_idx, batch_cnt)) return 1;
@@ -4149,7 +3909,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             v.ord = d.ord; v.perm = d.perm;
             const int cap = h->use_tc ? h->tc_grid : h->eval_grid;
             const int grid_ev = d.E < cap ? d.E : cap;
-            if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
+            if (h->use_tc2) { if (b2e_tc2_launch(&d, &a, 1, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed"); }
+            else if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
             else if (h->eval_bulk) eval_bulk_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
@@ -4224,7 +3985,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         goto after_pipeline;
     }
     mark(0);
-    if (h->use_tc) {
+    if (h->use_tc2) {
+        if (b2e_tc2_launch(&d, &a, 0, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed");
+    } else if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
         if (h->eval_bulk && h->fuse_update) eval_bulk_kernel<false, true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
@@ -4245,7 +4008,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     if (h->fuse_update && h->eval_bulk && h->use_eval_kernel && !h->use_tc) h->launches--;   // the first eval did it
     else update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
-    if (h->use_tc) {
+    if (h->use_tc2) {
+        if (b2e_tc2_launch(&d, &a, 1, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed");
+    } else if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
         if (h->eval_bulk) eval_bulk_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
@@ -4281,6 +4046,14 @@ after_pipeline:
     info_finalize_kernel<<<(d.E + 127) / 128, 128, 0, main_s>>>(d, a);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
+    if (h->use_tc2 && h->tc2_check) {                        // debugging aid: did the kernel's watchdog fire?
+        int dbg[4] = {0, 0, 0, 0};
+        CUDA_TRY(h, cudaStreamSynchronize(main_s));
+        CUDA_TRY(h, cudaMemcpy(dbg, h->tc2_dbg, sizeof(dbg), cudaMemcpyDeviceToHost));
+        if (dbg[0] != 0)
+            return fail(h, "tcgen05 eval kernel: watchdog fired, wait code " + std::to_string(dbg[0]) + " block " +
+                               std::to_string(dbg[1]) + " thread " + std::to_string(dbg[2]) + " parity " + std::to_string(dbg[3]));
+    }
     {   // g buffers ping-pong: what was g_t is now the newest raw-history gradient
         float *t = d.gprev; d.gprev = d.gnext; d.gnext = t;
     }
@@ -4296,17 +4069,28 @@ after_pipeline:
 int b2e_eval(b2e_handle h, const int32_t *batch_idx, const int32_t *batch_cnt, float *grad_out,
              float *loss_out, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (!grad_out || !loss_out) return fail(h, "b2e_eval: null pointer");
     if (check_ready(h, batch_idx, batch_cnt)) return 1;
     StepArgs a;
     memset(&a, 0, sizeof(a));
     a.mode = MODE_EVAL; a.ext_idx = batch_idx; a.ext_cnt = batch_cnt;
     a.grad_out = grad_out; a.loss_out = loss_out;
+    if (h->use_tc2) {
+        // the tensor-core eval kernel writes padded rows into the (idle) g_t buffer; copy them out
+        a.e_begin = 0; a.e_count = h->d.E;
+        if (b2e_tc2_launch(&h->d, &a, 0, h->tc2_grid, h->tc2_dbg, stream)) return fail(h, "tc2 launch failed");
+        strided_copy_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(h->d.gnext, grad_out, h->d.E, h->d.P, h->d.Pp, 1);
+        h->launches += 2;
+        CUDA_TRY(h, cudaGetLastError());
+        return 0;
+    }
     return launch(h, a, stream);
 }
 
 static int state_io(b2e_handle h, int which, void *user, size_t bytes, void *stream, int to_user) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (!user) return fail(h, "b2e_get/set_state: null pointer");
     Dev &d = h->d;
     cudaStream_t s = (cudaStream_t)stream;
@@ -4355,6 +4139,7 @@ int b2e_set_state(b2e_handle h, int which, const void *src, size_t bytes, void *
 
 int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (!idx_out || !cnt_out) return fail(h, "b2e_get_batch_indices: null pointer");
     if (!h->ord || !h->stream_bound) return fail(h, "b2e_get_batch_indices: no internal index stream");
     batch_indices_kernel<<<h->d.E, 64, 0, (cudaStream_t)stream>>>(h->d, idx_out, cnt_out);
@@ -4365,6 +4150,7 @@ int b2e_get_batch_indices(b2e_handle h, int32_t *idx_out, int32_t *cnt_out, void
 
 int b2e_set_trace(b2e_handle h, int enabled) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (enabled)
         for (auto &ev : h->tr)
             if (!ev && cudaEventCreate(&ev) != cudaSuccess) return fail(h, "b2e_set_trace: cudaEventCreate failed");
@@ -4375,6 +4161,7 @@ int b2e_set_trace(b2e_handle h, int enabled) {
 
 int b2e_get_trace(b2e_handle h, float *ms_out, int capacity) {
     if (!h || !ms_out) return -1;
+    DeviceGuard guard(h->cfg.device);
     int n = h->tr_count < capacity ? h->tr_count : capacity;
     for (int i = 0; i < n; ++i) {
         if (cudaEventSynchronize(h->tr[i + 1]) != cudaSuccess ||
@@ -4385,6 +4172,7 @@ int b2e_get_trace(b2e_handle h, float *ms_out, int capacity) {
 
 int b2e_next_batch(b2e_handle h, const uint8_t *env_mask, void *stream) {
     if (!h) return 1;
+    DeviceGuard guard(h->cfg.device);
     if (!h->ord || !h->stream_bound) return fail(h, "b2e_next_batch: no internal index stream");
     next_batch_kernel<<<h->d.E, 256, 0, (cudaStream_t)stream>>>(h->d, env_mask);
     h->launches++;

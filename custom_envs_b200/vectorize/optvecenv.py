@@ -109,8 +109,12 @@ class DeviceOptVecEnv(VecEnv):
 
     ``step_async`` copies the actions host->device from pinned memory and launches the
     fused step; ``step_wait`` copies observations / rewards / dones / infos device->host
-    into pinned buffers.  The returned ``states`` array is a view of that pinned buffer
-    (valid until the next ``step_wait``/``reset``) unless ``copy_outputs=True``."""
+    into pinned buffers.  ``rewards`` / ``terminals`` / ``infos`` are fresh objects every step
+    (the stable-baselines runners append them to their rollout lists without copying).  The
+    ``states`` array alone is a view of the pinned observation buffer, valid until the next
+    ``step_wait`` / ``reset`` -- the runners copy observations themselves (``self.obs[:] = obs``,
+    ``mb_obs.append(self.obs.copy())``) -- unless ``copy_outputs=True`` asks for a private copy of
+    the 60-byte-per-agent matrix as well."""
 
     def __init__(self, batched_env, observation_space=None, action_space=None, callbacks=(),
                  copy_outputs=False, direct_host_obs=None):
@@ -147,9 +151,11 @@ class DeviceOptVecEnv(VecEnv):
         self._done_host = torch.empty(envs, dtype=torch.uint8, **pin)
         self._info_host = torch.empty((envs, 16), dtype=torch.float64, **pin)
         # the VecEnv surface repeats reward / done once per agent row (optvecenv.py:43-45): host
-        # threads expand the per-env values while the observation copy is still on the wire
-        self._rew_rows_np = np.empty(rows, dtype=np.float32)
-        self._done_rows_np = np.empty(rows, dtype=np.bool_)
+        # threads expand the per-env values while the observation copy is still on the wire.
+        # FRESH arrays every step, like the reference's np.stack: PPO2 / A2C runners keep
+        # ``rewards`` / ``dones`` of every step of a rollout without copying them.
+        self._rew_rows_np = None
+        self._done_rows_np = None
         self._scalars_event = torch.cuda.Event()
         self._event = torch.cuda.Event()
 
@@ -158,15 +164,15 @@ class DeviceOptVecEnv(VecEnv):
         return states.copy() if self.copy_outputs else states
 
     def _row_outputs(self):
-        """(rewards[rows], terminals[rows]); buffers reused by the next step unless copy_outputs."""
-        if self.copy_outputs:
-            return self._rew_rows_np.copy(), self._done_rows_np.copy()
+        """(rewards[rows], terminals[rows]): arrays allocated for this step, never reused."""
         return self._rew_rows_np, self._done_rows_np
 
     def _expand_rows(self):
         envs, agents = self.env.num_envs, self.env.num_params
         reward = self._rew_host.numpy()
         done = self._done_host.numpy().astype(np.bool_)
+        self._rew_rows_np = np.empty(envs * agents, dtype=np.float32)
+        self._done_rows_np = np.empty(envs * agents, dtype=np.bool_)
         rew_rows = self._rew_rows_np.reshape(envs, agents)
         done_rows = self._done_rows_np.reshape(envs, agents)
 

@@ -131,6 +131,32 @@ def test_optvecenv_fuses_monitored_envs():
         assert len(frame) == 2 and set(keys) <= set(frame.columns) and list(frame['l']) == [5, 5]
 
 
+def test_optvecenv_step_outputs_survive_the_next_step():
+    """stable-baselines' runners do ``mb_rewards.append(rewards)`` / ``mb_dones.append(self.dones)``
+    without copying (ppo2.py Runner.run), so the rewards / terminals / infos of step N must not be
+    rewritten by step N+1 (the reference returns fresh ``np.stack`` results, optvecenv.py:78-88)."""
+    from custom_envs.vectorize import OptVecEnv
+    from custom_envs_b200.compat import make
+    from custom_envs import load_data
+    data = load_data('iris', 32)
+    fns = [partial(make, 'MultiOptLRs-v0', problem='nn', max_batches=3,
+                   problem_kwargs=dict(layers=(), data_set=data)) for _ in range(3)]
+    vec = OptVecEnv(fns)
+    vec.reset()
+    kept, snapshots = [], []
+    for t in range(5):
+        actions = np.random.RandomState(t).uniform(0, 2, size=(45, 1)).astype(np.float32)
+        _, rewards, terminals, infos = vec.step(actions)
+        kept.append((rewards, terminals, infos[0]))
+        snapshots.append((rewards.copy(), terminals.copy(), dict(infos[0])))
+    for (rewards, terminals, info), (rew_then, term_then, info_then) in zip(kept, snapshots):
+        assert np.array_equal(rewards, rew_then) and np.array_equal(terminals, term_then)
+        assert info == info_then
+    assert len({id(k[0]) for k in kept}) == 5 and len({id(k[1]) for k in kept}) == 5
+    assert not np.array_equal(kept[0][0], kept[1][0])
+    vec.close()
+
+
 def test_vectorised_monitor_path_equals_per_env_replay():
     """A callback-free Monitor around every env takes the vectorised bookkeeping path of the fused
     OptVecEnv; a Monitor with a callback forces the per-env replay.  Same seeds -> same outputs,
