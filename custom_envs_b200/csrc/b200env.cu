@@ -3186,8 +3186,7 @@ struct b2e_env {
     size_t smem_tc;
     int tc_grid;
     bool use_tc2;                    // warp-specialised tcgen05 eval kernel (b200tc.cu)
-    int tc2_grid;
-    int *tc2_dbg;                    // watchdog word of that kernel (device memory)
+    b2e_tc2_ctx *tc2;                // its context: tensor map, watchdog word, grid
     bool tc2_check;                  // B2E_TC_CHECK=1: synchronise and test the watchdog after every step
     float *w2, *g2, *ws;
     int obs_stages, obs_regs, obs_bulk;        // obs_kernel2 variant (0 stages = obs_kernel)
@@ -3587,7 +3586,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     for (auto &ev : h->tr) ev = nullptr;
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
-    h->use_tc2 = false; h->tc2_grid = 0; h->tc2_dbg = nullptr; h->tc2_check = false;
+    h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
     h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
@@ -3692,15 +3691,11 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (occ_tc > 512 / tc::TMEM_COLS) occ_tc = 512 / tc::TMEM_COLS;    // TMEM: 512 columns per SM
         h->tc_grid = occ_tc * h->num_sms;
     }
-    {   // tcgen05 eval kernel, warp-specialised (B2E_TC=2)
+    {   // tcgen05 eval kernel, warp-specialised (B2E_TC=2); its context is made once the state
+        // buffers exist (the tensor map holds the address of w)
         const char *tcv = getenv("B2E_TC");
         h->use_tc2 = h->use_eval_kernel && tcv && atoi(tcv) == 2 && b2e_tc2_supported(&h->d);
         if (h->use_tc2) {
-            const char *err = b2e_tc2_prepare();
-            if (err) return bail(std::string("b2e_create: ") + err);
-            if (cudaMalloc((void **)&h->tc2_dbg, 64) != cudaSuccess || cudaMemset(h->tc2_dbg, 0, 64) != cudaSuccess)
-                return bail("b2e_create: cudaMalloc of the watchdog word failed");
-            h->tc2_grid = cfg->num_envs < h->num_sms ? cfg->num_envs : h->num_sms;
             h->tc2_check = getenv("B2E_TC_CHECK") && atoi(getenv("B2E_TC_CHECK")) != 0;
             h->use_tc = false;
         }
@@ -3798,6 +3793,11 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part; d.part_u = h->part_u;
     d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc; d.w2 = h->w2; d.g2 = h->g2; d.ws = h->ws;
     d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param; d.param_of_row = h->param_of_row;
+    if (h->use_tc2) {
+        std::string err;
+        h->tc2 = b2e_tc2_create(&h->d, h->num_sms, &err);
+        if (!h->tc2) return bail("b2e_create: " + err);
+    }
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
@@ -3809,7 +3809,8 @@ void b2e_destroy(b2e_handle h) {
     DeviceGuard guard(h->cfg.device);
     cudaFree(h->X); cudaFree(h->targets_f); cudaFree(h->labels); cudaFree(h->ord); cudaFree(h->perm);
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
-    cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws); cudaFree(h->tc2_dbg);
+    cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws);
+    b2e_tc2_destroy(h->tc2);
     cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
@@ -3909,7 +3910,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             v.ord = d.ord; v.perm = d.perm;
             const int cap = h->use_tc ? h->tc_grid : h->eval_grid;
             const int grid_ev = d.E < cap ? d.E : cap;
-            if (h->use_tc2) { if (b2e_tc2_launch(&d, &a, 1, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed"); }
+            if (h->use_tc2) { if (b2e_tc2_launch(h->tc2, &d, &a, 1, main_s)) return fail(h, "tc2 launch failed"); }
             else if (h->use_tc) tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(v, a);
             else if (h->eval_bulk) eval_bulk_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
             else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(v, a);
@@ -3986,7 +3987,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     }
     mark(0);
     if (h->use_tc2) {
-        if (b2e_tc2_launch(&d, &a, 0, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed");
+        if (b2e_tc2_launch(h->tc2, &d, &a, 0, main_s)) return fail(h, "tc2 launch failed");
     } else if (h->use_tc) {
         tc_eval_kernel<false><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
@@ -4009,7 +4010,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     else update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
     if (h->use_tc2) {
-        if (b2e_tc2_launch(&d, &a, 1, h->tc2_grid, h->tc2_dbg, main_s)) return fail(h, "tc2 launch failed");
+        if (b2e_tc2_launch(h->tc2, &d, &a, 1, main_s)) return fail(h, "tc2 launch failed");
     } else if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);
     } else if (h->use_eval_kernel) {
@@ -4049,7 +4050,7 @@ after_pipeline:
     if (h->use_tc2 && h->tc2_check) {                        // debugging aid: did the kernel's watchdog fire?
         int dbg[4] = {0, 0, 0, 0};
         CUDA_TRY(h, cudaStreamSynchronize(main_s));
-        CUDA_TRY(h, cudaMemcpy(dbg, h->tc2_dbg, sizeof(dbg), cudaMemcpyDeviceToHost));
+        if (b2e_tc2_watchdog(h->tc2, dbg)) return fail(h, "tcgen05 eval kernel: cannot read the watchdog word");
         if (dbg[0] != 0)
             return fail(h, "tcgen05 eval kernel: watchdog fired, wait code " + std::to_string(dbg[0]) + " block " +
                                std::to_string(dbg[1]) + " thread " + std::to_string(dbg[2]) + " parity " + std::to_string(dbg[3]));
@@ -4079,7 +4080,7 @@ int b2e_eval(b2e_handle h, const int32_t *batch_idx, const int32_t *batch_cnt, f
     if (h->use_tc2) {
         // the tensor-core eval kernel writes padded rows into the (idle) g_t buffer; copy them out
         a.e_begin = 0; a.e_count = h->d.E;
-        if (b2e_tc2_launch(&h->d, &a, 0, h->tc2_grid, h->tc2_dbg, stream)) return fail(h, "tc2 launch failed");
+        if (b2e_tc2_launch(h->tc2, &h->d, &a, 0, stream)) return fail(h, "tc2 launch failed");
         strided_copy_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(h->d.gnext, grad_out, h->d.E, h->d.P, h->d.Pp, 1);
         h->launches += 2;
         CUDA_TRY(h, cudaGetLastError());

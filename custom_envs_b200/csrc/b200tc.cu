@@ -10,16 +10,17 @@
 // and N, so one MMA per K step yields all four split products (lo.lo included: with truncation the
 // lo parts are one-sided and their product is not negligible).
 //
-// Persistent, one 512-thread CTA per SM, warp-specialised; envs e = blockIdx.x + k * gridDim.x:
-//   warp 0      W producer  : W1 tile [32 f][64 j] of the forward unit -> stage, 16-byte cp.async
-//   warp 1      XF producer : minibatch rows [32 s][32 f] of the forward unit (gather), cp.async
-//   warp 2      XB producer : minibatch rows [32 s][128 f] of a backward tile (L2 hits), cp.async
-//   warp 3      MMA issuer  : one elected lane; forward of env k+1 is issued BEFORE backward of env k,
-//                             so the tail of env k runs under the forward loads / MMAs of env k+1
+// Persistent, one 768-thread CTA per SM, warp-specialised; envs e = blockIdx.x + k * gridDim.x:
+//   warp 0      L2 prefetcher : the next env's parameters, one env ahead of the forward stream
+//   warp 1      (spare)
+//   warps 3, 23 MMA issuers : forward units / backward tiles, one elected lane each, two independent
+//                             in-order queues; the tail of env k runs under the forward stream of env k+1
 //   warps 4-7   tail        : TMEM -> Hpre, bias/relu/layer 2/softmax-CE/backward -> dPre operand
 //   warps 8-11  drain       : gradient tiles TMEM -> registers -> shared-memory transpose -> HBM;
 //                             second eval: the step's scalars (reward, done, info, cursor)
-//   warps 12-15 converters  : lo parts of every landed operand tile
+//   warps 12-19 forward converters : lo part of the landed W1 tile; the unit's minibatch rows [32 s][32 f] are
+//                             loaded by these threads (L2 -> register, two units ahead) and stored as hi + lo
+//   warps 2, 20-22 backward converters : rows [32 s][128 f] of a backward tile, L2 -> register -> hi + lo
 // Pipelines: forward ring (4 stages x 24 KB: W hi/lo, X hi/lo), backward ring (2 x 32 KB: X hi/lo),
 // both full -> converted -> (tcgen05.commit) empty; TMEM: four forward accumulators [128 x 64] (every
 // fourth unit each: the tensor core's adder truncates, so long sums are split and added by threads) and
@@ -31,9 +32,13 @@
 //     SBO = 512 (4-row groups), LBO = 4096 (next 32 MN elements)
 //   K-major tf32 (X as B of the forward): rows [N][32 K elements], 16-byte chunks XORed with
 //     (row & 7) (SWIZZLE_128B), SBO = 1024
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <string>
 
 #include "b200env_shared.cuh"
 #include "b200tc.h"
@@ -53,17 +58,20 @@ constexpr int OFF_TAIL = OFF_G + 16384;               // float scratch of the ta
 // tail scratch (floats)
 constexpr int CMAX = 16;
 constexpr int TW_MAX = N1 + N1 * CMAX + CMAX;         // b1, W2, b2
-constexpr int T_H = 0, T_TW = T_H + B * N1, T_TG = T_TW + TW_MAX, T_Z = T_TG + TW_MAX, T_LB = T_Z + B * CMAX,
-              T_YS = T_LB + B, T_GP = T_YS + B, T_MISC = T_GP + 2 * N1, T_END = T_MISC + 16;
+constexpr int HS = B + 1;                             // row stride of the transposed activations H^T [64 j][32 s]
+constexpr int T_H = 0, T_TW = T_H + N1 * HS, T_TG = T_TW + TW_MAX, T_ZP = T_TG + TW_MAX, T_Z = T_ZP + 4 * CMAX * B,
+              T_YS = T_Z + B * CMAX, T_GP = T_YS + B, T_MISC = T_GP + 2 * N1, T_END = T_MISC + 16;
 constexpr int SMEM_BYTES = OFF_TAIL + T_END * 4 + 1024;   // + slack to align the base to 1024 bytes
 constexpr int TMEM_COLS = 512;                        // forward 4 x 64, gradient 2 x 128 columns
 constexpr int TM_F = 0, TM_G = 256, NACC = 4;
-constexpr int THREADS = 512;
+constexpr int THREADS = 768;                          // 24 warps, at most 80 registers each
+constexpr int CONV_F_WARPS = 8, CONV_B_WARPS = 4, MMA_B_WARP = 23;   // backward converters: warps 2, 20, 21, 22
+constexpr int DBG_BYTES = 64 + 8 * 512 * 8;
 constexpr long long WATCHDOG_CYCLES = 1500000000LL;   // ~0.8 s: a wait this long is a protocol bug
 
 struct Bars {
-    uint64_t fullF[SF], convF[SF], emptyF[SF];
-    uint64_t fullB[SB], convB[SB], emptyB[SB];
+    uint64_t convF[SF], emptyF[SF];
+    uint64_t convB[SB], emptyB[SB];
     uint64_t g_full[2], g_free[2], tail_done[2];
     uint64_t fwd_done, fwd_free, dpre_ready, dpre_free;
 };
@@ -94,11 +102,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int co
         }
     }
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {       // arrive when this thread's copies have landed
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void prefetch_l2(const void *src, int bytes) {              // bytes: multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
@@ -131,6 +136,12 @@ __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 1
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
                  : "r"(taddr))
 
+#define TC2_LD16(taddr, v) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(taddr))
+
 // lo part of the 3xTF32 split: the tensor core sees trunc(x) of the raw word, lo carries the rest,
 // itself rounded to nearest at tf32 precision (its own truncation would be one-sided)
 __device__ __forceinline__ float lo_of(float x) {
@@ -145,7 +156,9 @@ __device__ __forceinline__ uint32_t swz16(int q, int r) { return (uint32_t)((q ^
 
 template <bool SECOND, int CC>
 __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_constant__ Dev d,
-                                                              const __grid_constant__ StepArgs a, int *dbg) {
+                                                              const __grid_constant__ StepArgs a,
+                                                                                                                            const __grid_constant__ CUtensorMap map_g0,
+                                                              const __grid_constant__ CUtensorMap map_g1, int gsel, int pf_units, int *dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) Bars bars;
     __shared__ uint32_t tmem_slot;
@@ -160,10 +173,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
     const int D = d.D, C = CC ? CC : d.C;
     const int UF = (D + 31) >> 5, TB = (D + 127) >> 7;
     const int e_end = a.e_begin + a.e_count;
+    // optional timeline of CTA 0 (B2E_TC_TRACE=<file>): clock64 of the n-th event of each role
+    long long *const trace = (dbg[15] != 0 && blockIdx.x == 0) ? reinterpret_cast<long long *>(dbg + 16) : nullptr;
+#define TC2_TRACE(role, n) do { if (trace && lane == 0 && (n) < 512) trace[(role) * 512 + (n)] = clock64(); } while (0)
 
     if (tid == 0) {
-        for (int s = 0; s < SF; ++s) { mbar_init(&bars.fullF[s], 64); mbar_init(&bars.convF[s], 4); mbar_init(&bars.emptyF[s], 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(&bars.fullB[s], 32); mbar_init(&bars.convB[s], 4); mbar_init(&bars.emptyB[s], 1); }
+        for (int s = 0; s < SF; ++s) { mbar_init(&bars.convF[s], CONV_F_WARPS); mbar_init(&bars.emptyF[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&bars.convB[s], CONV_B_WARPS); mbar_init(&bars.emptyB[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars.g_full[s], 1); mbar_init(&bars.g_free[s], 4); mbar_init(&bars.tail_done[s], 1);
         }
@@ -181,163 +197,134 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        // ===================== W producer: forward unit u = rows f in [32u, 32u + 32) of W1, both column halves
-        uint32_t it = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
-            const float *We = d.w + (size_t)e * d.Pp;
-            for (int u = 0; u < UF; ++u, ++it) {
-                const int s = it % SF;
-                mbar_wait(&bars.emptyF[s], ((it / SF) & 1) ^ 1, 1, dbg);
-                const uint32_t base = sbase + OFF_F + s * F_STAGE + F_W;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = i * 32 + lane, r = c >> 4, q = c & 15, f = 32 * u + r;
-                    cp_async16(base + (q >> 3) * 4096 + r * 128 + swz32(q & 7, r),
-                               We + (size_t)(f < D ? f : 0) * N1 + 4 * q, f < D ? 16 : 0);
-                }
-                cp_async_arrive(&bars.fullF[s]);
-            }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 1) {
-        // ===================== XF producer: forward unit u = features [32u, 32u + 32) of the 32 minibatch rows
-        uint32_t it = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
-            const int *idx; int cnt;
-            current_batch(d, a, e, d.sc + e, idx, cnt);
-            const int my_row = lane < cnt ? idx[lane] : -1;
-            for (int u = 0; u < UF; ++u, ++it) {
-                const int s = it % SF;
-                mbar_wait(&bars.emptyF[s], ((it / SF) & 1) ^ 1, 2, dbg);
-                const uint32_t base = sbase + OFF_F + s * F_STAGE + F_X;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int sr = i * 4 + (lane >> 3), q = lane & 7, f = 32 * u + 4 * q;
-                    const int row = __shfl_sync(0xffffffffu, my_row, sr);
-                    const bool ok = row >= 0 && f < D;
-                    cp_async16(base + sr * 128 + swz16(q, sr), d.X + (ok ? (size_t)row * d.Dp + f : 0), ok ? 16 : 0);
-                }
-                cp_async_arrive(&bars.fullF[s]);
-            }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 2) {
-        // ===================== XB producer: backward tile t = features [128t, 128t + 128), four 32-feature blocks
-        uint32_t it = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
-            const int *idx; int cnt;
-            current_batch(d, a, e, d.sc + e, idx, cnt);
-            const int my_row = lane < cnt ? idx[lane] : -1;
-            for (int t = 0; t < TB; ++t, ++it) {
-                const int s = it % SB;
-                mbar_wait(&bars.emptyB[s], ((it / SB) & 1) ^ 1, 3, dbg);
-                const uint32_t base = sbase + OFF_B + s * B_STAGE;
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int blk = i >> 3, sr = (i & 7) * 4 + (lane >> 3), q = lane & 7, f = 128 * t + 32 * blk + 4 * q;
-                    const int row = __shfl_sync(0xffffffffu, my_row, sr);
-                    const bool ok = row >= 0 && f < D;
-                    cp_async16(base + blk * 4096 + sr * 128 + swz32(q, sr), d.X + (ok ? (size_t)row * d.Dp + f : 0), ok ? 16 : 0);
-                }
-                cp_async_arrive(&bars.fullB[s]);
-            }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 3) {
-        // ===================== MMA issuer
-        constexpr uint32_t TF32 = (1u << 4) | (2u << 7) | (2u << 10);
-        const uint32_t idesc_f = TF32 | (1u << 15) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);               // A MN-major, B K-major
-        const uint32_t idesc_b = TF32 | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); // both MN-major
-        uint32_t itF = 0, itB = 0, itG = 0;
-        const uint64_t dpd = make_desc(sbase + OFF_DP, 4096, 512, 1);
-        auto backward = [&](int j) {                     // j = local index of the env whose dPre is ready
-            mbar_wait(&bars.dpre_ready, j & 1, 4, dbg);
-            for (int t = 0; t < TB; ++t, ++itB, ++itG) {
-                const int s = itB % SB, g = itG & 1;
-                mbar_wait(&bars.convB[s], (itB / SB) & 1, 5, dbg);
-                mbar_wait(&bars.g_free[g], ((itG >> 1) & 1) ^ 1, 6, dbg);
-                fence_async();
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t ahi = make_desc(sbase + OFF_B + s * B_STAGE, 4096, 512, 1);
-                    const uint64_t alo = make_desc(sbase + OFF_B + s * B_STAGE + B_XLO, 4096, 512, 1);
-                    const uint32_t acc = tmem + TM_G + 128 * g;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {     // 8 samples per MMA = 1024 bytes of each block
-                        mma_tf32(acc, ahi + (uint64_t)(kk * 64), dpd + (uint64_t)(kk * 64), idesc_b, kk ? 1u : 0u);
-                        mma_tf32(acc, alo + (uint64_t)(kk * 64), dpd + (uint64_t)(kk * 64), idesc_b, 1u);
-                    }
-                    mma_commit(&bars.emptyB[s]);
-                    mma_commit(&bars.g_full[g]);
-                    if (t == TB - 1) mma_commit(&bars.dpre_free);
-                }
-                __syncwarp();
-            }
+        // ===================== L2 prefetcher.  The forward operands reach shared memory through the
+        // converter threads' registers (this SM's copy engine retires one bulk tensor copy per ~360
+        // cycles whatever its size up to 4 KB -- profiles/tools/tma_rate_probe.cu -- which is a third
+        // of the rate the HBM share of an SM needs), so the bytes in flight are bounded by registers and
+        // the loads must be L2 hits: this warp requests W1 and the tail parameters of env k+1 while env
+        // k streams (203 KB per SM, 30 MB for the whole GPU, one env ahead).
+        auto prefetch_env = [&](int e) {
+            const char *base = reinterpret_cast<const char *>(d.w + (size_t)e * d.Pp);
+            const int lines = (d.P * 4 + 127) >> 7;
+            for (int i = lane; i < lines; i += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
         };
         int k = 0;
+        if (a.e_begin + (int)blockIdx.x < e_end && pf_units > 0) prefetch_env(a.e_begin + blockIdx.x);
         for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
-            mbar_wait(&bars.fwd_free, (k & 1) ^ 1, 7, dbg);       // the tail has read the accumulators of env k-1
-            for (int u = 0; u < UF; ++u, ++itF) {
-                const int s = itF % SF;
-                mbar_wait(&bars.convF[s], (itF / SF) & 1, 8, dbg);
-                fence_async();
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t ad = make_desc(sbase + OFF_F + s * F_STAGE + F_W, 4096, 512, 1);
-                    const uint64_t bd = make_desc(sbase + OFF_F + s * F_STAGE + F_X, 16, 1024, 2);
-                    // The tensor core's adder truncates: a sum over all 98 K steps in ONE accumulator
-                    // drifts by ~1e-6 of the result.  Four accumulators take every fourth unit
-                    // (<= 28 steps each) and the tail adds them in fp32 round-to-nearest.
-                    const uint32_t acc = tmem + TM_F + 64 * (u & (NACC - 1));
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)       // 8 features per MMA: 1024 bytes of A, 32 bytes of B
-                        mma_tf32(acc, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 2), idesc_f, (u >= NACC || kk) ? 1u : 0u);
-                    mma_commit(&bars.emptyF[s]);
-                    if (u == UF - 1) mma_commit(&bars.fwd_done);
-                }
-                __syncwarp();
-            }
-            if (k >= 1) backward(k - 1);
+            if (e + (int)gridDim.x < e_end && pf_units > 0) prefetch_env(e + gridDim.x);
+            mbar_wait(&bars.fwd_done, k & 1, 1, dbg);     // pace: one env ahead of the forward stream
         }
-        if (k >= 1) backward(k - 1);
-    } else if (warp < 8) {
+    } else if (warp == 3 || warp == MMA_B_WARP) {
+        // ===================== MMA issuers: warp 3 the forward units, warp 23 the backward tiles.  Two
+        // in-order queues with blocking waits; a backward tile that is not ready (dPre, accumulator
+        // not drained) never holds up the forward stream, which is what keeps HBM busy.  Each warp's
+        // tcgen05.commit covers the MMAs its own elected lane issued.
+        constexpr uint32_t TF32 = (1u << 4) | (2u << 7) | (2u << 10);
+        if (warp == 3) {
+            const uint32_t idesc_f = TF32 | (1u << 15) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A MN-major, B K-major
+            const uint64_t ad0 = make_desc(sbase + OFF_F + F_W, 4096, 512, 1);
+            const uint64_t bd0 = make_desc(sbase + OFF_F + F_X, 16, 1024, 2);
+            uint32_t itF = 0;
+            int k = 0;
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+                mbar_wait(&bars.fwd_free, (k & 1) ^ 1, 7, dbg);   // the tail has read the accumulators of env k-1
+                for (int u = 0; u < UF; ++u, ++itF) {
+                    const int s = itF % SF;
+                    mbar_wait(&bars.convF[s], (itF / SF) & 1, 8, dbg);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = ad0 + (uint64_t)(s * (F_STAGE >> 4)), bd = bd0 + (uint64_t)(s * (F_STAGE >> 4));
+                        // The tensor core's adder truncates: a sum over all 98 K steps in ONE accumulator
+                        // drifts by ~1e-6 of the result.  Four accumulators take every fourth unit
+                        // (<= 28 steps each) and the tail adds them in fp32 round-to-nearest.
+                        const uint32_t acc = tmem + TM_F + 64 * (u & (NACC - 1));
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)   // 8 features per MMA: 1024 bytes of A, 32 bytes of B
+                            mma_tf32(acc, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 2), idesc_f, (u >= NACC || kk) ? 1u : 0u);
+                        mma_commit(&bars.emptyF[s]);
+                        if (u == UF - 1) mma_commit(&bars.fwd_done);
+                    }
+                    __syncwarp();
+                    TC2_TRACE(3, itF);
+                }
+            }
+        } else {
+            const uint32_t idesc_b = TF32 | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // both MN-major
+            const uint64_t dpd = make_desc(sbase + OFF_DP, 4096, 512, 1);
+            const uint64_t ahi0 = make_desc(sbase + OFF_B, 4096, 512, 1), alo0 = make_desc(sbase + OFF_B + B_XLO, 4096, 512, 1);
+            uint32_t itB = 0;
+            int k = 0;
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+                mbar_wait(&bars.dpre_ready, k & 1, 4, dbg);
+                for (int t = 0; t < TB; ++t, ++itB) {
+                    const int s = itB % SB, g = itB & 1;
+                    mbar_wait(&bars.convB[s], (itB / SB) & 1, 5, dbg);
+                    mbar_wait(&bars.g_free[g], ((itB >> 1) & 1) ^ 1, 6, dbg);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ahi = ahi0 + (uint64_t)(s * (B_STAGE >> 4)), alo = alo0 + (uint64_t)(s * (B_STAGE >> 4));
+                        const uint32_t acc = tmem + TM_G + 128 * g;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) { // 8 samples per MMA = 1024 bytes of each block
+                            mma_tf32(acc, ahi + (uint64_t)(kk * 64), dpd + (uint64_t)(kk * 64), idesc_b, kk ? 1u : 0u);
+                            mma_tf32(acc, alo + (uint64_t)(kk * 64), dpd + (uint64_t)(kk * 64), idesc_b, 1u);
+                        }
+                        mma_commit(&bars.emptyB[s]);
+                        mma_commit(&bars.g_full[g]);
+                        if (t == TB - 1) mma_commit(&bars.dpre_free);
+                    }
+                    __syncwarp();
+                    TC2_TRACE(4, itB);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ===================== tail group (128 threads, named barrier 1)
         const int q = warp - 4, ttid = tid - 128;
-        float *Hb = ts + T_H, *tw = ts + T_TW, *tg = ts + T_TG, *Z = ts + T_Z, *lb = ts + T_LB, *gp = ts + T_GP;
+        // scratch: HT [64 j][33] hidden activations (transposed, odd stride: lanes along j or along s
+        // are both conflict free); tw = b1 | W2 padded to 16 classes per row | b2; tg = tail gradient
+        // in parameter order; Zp [4][16][32] partial logits; dZ [32][16]
+        float *HT = ts + T_H, *tw = ts + T_TW, *tg = ts + T_TG, *Zp = ts + T_ZP, *dZ = ts + T_Z, *gp = ts + T_GP;
         int *ys = reinterpret_cast<int *>(ts + T_YS);
         float *tmisc = ts + T_MISC;
-        const int Zs = CMAX;
         const int tailP = d.tailP;
-        const float *b1 = tw, *W2 = tw + N1, *b2 = tw + N1 + N1 * C;
+        const float *b1 = tw, *W2p = tw + N1, *b2 = tw + N1 + N1 * CMAX;
         unsigned char *dP = sm + OFF_DP;
+        constexpr int C4 = CC ? (CC + 3) / 4 : CMAX / 4;  // float4 groups of a padded class row that hold data
+        for (int i = ttid; i < N1 * CMAX; i += 128)       // the padding of the W2 rows multiplies zeros of dZ: keep it finite
+            if (i % CMAX >= C) tw[N1 + i] = 0.f;
         int k = 0;
         for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
             const float *We = d.w + (size_t)e * d.Pp;
             float *gout = d.gnext + (size_t)e * d.Pp;
             const int *idx; int cnt;
             current_batch(d, a, e, d.sc + e, idx, cnt);
-            for (int i = ttid; i < tailP; i += 128) tw[i] = We[d.P1 + i];
+            for (int i = ttid; i < tailP; i += 128) {     // b1, W2 (rows padded to 16), b2
+                const float v = We[d.P1 + i];
+                const int r = i - N1;
+                if (i < N1) tw[i] = v;
+                else if (r < N1 * C) tw[N1 + (r / C) * CMAX + (r % C)] = v;
+                else tw[N1 + N1 * CMAX + (r - N1 * C)] = v;
+            }
             if (ttid < B) ys[ttid] = ttid < cnt ? d.labels[idx[ttid]] : 0;
-            // ---- forward accumulator: lanes 0..63 = W_hi rows, 64..127 = W_lo rows; columns 0..31 = X_hi, 32..63 = X_lo
+            // ---- forward accumulators: lanes 0..63 = W_hi rows, 64..127 = W_lo rows; columns 0..31 = X_hi, 32..63 = X_lo
             mbar_wait(&bars.fwd_done, k & 1, 9, dbg);
+            if (q == 0) TC2_TRACE(5, 2 * k);
             tc_fence_after();
             float acc[32];
             {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_F;
                 const int nacc = UF < NACC ? UF : NACC;
-                float lo_part[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { acc[i] = 0.f; lo_part[i] = 0.f; }
-                for (int c = 0; c < nacc; ++c) {
-                    uint32_t v0[32], v1[32];
-                    TC2_LD32(taddr + 64 * c + 32, v1);
-                    TC2_LD32(taddr + 64 * c, v0);
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                for (int c = 0; c < 2 * nacc; ++c) {      // the X_lo halves of the accumulators first (small terms), then the X_hi halves
+                    uint32_t v[32];
+                    TC2_LD32(taddr + 64 * (c % nacc) + (c < nacc ? 32 : 0), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { lo_part[i] += __uint_as_float(v1[i]); acc[i] += __uint_as_float(v0[i]); }
+                    for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
                 }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] += lo_part[i];
             }
             tc_fence_before();
             __syncwarp();
@@ -345,74 +332,114 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             const int j = (q & 1) * 32 + lane;
             if (q >= 2) {
 #pragma unroll
-                for (int s = 0; s < B; ++s) Hb[s * N1 + j] = acc[s];
+                for (int s = 0; s < B; ++s) HT[j * HS + s] = acc[s];
             }
             group_bar(1);
             if (q < 2) {                                  // + bias, relu (rows the minibatch does not have stay 0)
                 const float bj = b1[j];
 #pragma unroll
                 for (int s = 0; s < B; ++s) {
-                    const float v = (Hb[s * N1 + j] + acc[s]) + bj;
-                    Hb[s * N1 + j] = (s < cnt && v > 0.f) ? v : 0.f;
+                    const float v = (HT[j * HS + s] + acc[s]) + bj;
+                    HT[j * HS + s] = (s < cnt && v > 0.f) ? v : 0.f;
                 }
             }
             group_bar(1);
-            // ---- second layer, softmax cross-entropy (optimize_nn.py:42-50)
-            for (int i = ttid; i < cnt * C; i += 128) {
-                const int s = i / C, c = i - s * C;
-                float z = b2[c];
-#pragma unroll 8
-                for (int jj = 0; jj < N1; ++jj) z = fmaf(Hb[s * N1 + jj], W2[jj * C + c], z);
-                Z[s * Zs + c] = z;
+            // ---- second layer (optimize_nn.py:42-44): lane = sample, warp = a quarter of the hidden units;
+            // the W2 rows are broadcast reads, 16 x C FMAs on C independent accumulators per thread
+            {
+                float z[4 * C4];
+#pragma unroll
+                for (int c = 0; c < 4 * C4; ++c) z[c] = 0.f;
+#pragma unroll 4
+                for (int jj = 0; jj < 16; ++jj) {
+                    const int jr = 16 * q + jj;
+                    const float h = HT[jr * HS + lane];
+#pragma unroll
+                    for (int c4 = 0; c4 < C4; ++c4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(W2p + jr * CMAX + 4 * c4);
+                        z[4 * c4] = fmaf(h, w.x, z[4 * c4]); z[4 * c4 + 1] = fmaf(h, w.y, z[4 * c4 + 1]);
+                        z[4 * c4 + 2] = fmaf(h, w.z, z[4 * c4 + 2]); z[4 * c4 + 3] = fmaf(h, w.w, z[4 * c4 + 3]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4 * C4; ++c) Zp[(q * CMAX + c) * B + lane] = z[c];
             }
             group_bar(1);
-            if (ttid < B) {
-                const int s = ttid;
+            // ---- softmax cross-entropy and its derivative (optimize_nn.py:47-50): warp 0, lane = sample
+            if (q == 0) {
+                float z[4 * C4];
+#pragma unroll
+                for (int c = 0; c < 4 * C4; ++c)
+                    z[c] = ((Zp[c * B + lane] + Zp[(CMAX + c) * B + lane]) + (Zp[(2 * CMAX + c) * B + lane] + Zp[(3 * CMAX + c) * B + lane])) +
+                           (c < C ? b2[c] : 0.f);
                 float loss = 0.f;
-                float *z = Z + s * Zs;
-                if (s < cnt) {
-                    const int y = ys[s];
+                if (lane < cnt) {
+                    const int y = ys[lane];
                     float m = z[0];
-                    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
-                    float sum = 0.f;
-                    for (int c = 0; c < C; ++c) sum += expf(z[c] - m);
-                    const float zy = z[y];
+#pragma unroll
+                    for (int c = 1; c < 4 * C4; ++c) if (c < C) m = fmaxf(m, z[c]);
+                    float sum = 0.f, zy = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4 * C4; ++c) if (c < C) { if (c == y) zy = z[c]; z[c] = expf(z[c] - m); sum += z[c]; }
                     loss = (m + logf(sum)) - zy;
                     const float inv = 1.0f / sum;
-                    for (int c = 0; c < C; ++c) {
-                        const float p = expf(z[c] - m) * inv;
-                        z[c] = p - (c == y ? 1.f : 0.f);
-                    }
+#pragma unroll
+                    for (int c = 0; c < 4 * C4; ++c) z[c] = c < C ? z[c] * inv - (c == y ? 1.f : 0.f) : 0.f;
                 } else {
-                    for (int c = 0; c < C; ++c) z[c] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4 * C4; ++c) z[c] = 0.f;
                 }
-                lb[s] = loss;
+#pragma unroll
+                for (int c4 = 0; c4 < C4; ++c4)
+                    *reinterpret_cast<float4 *>(dZ + lane * CMAX + 4 * c4) = make_float4(z[4 * c4], z[4 * c4 + 1], z[4 * c4 + 2], z[4 * c4 + 3]);
+                // loss = mean over the minibatch; gb2 = column sums of dZ: lanes are the samples
+                float lsum = loss;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+                if (lane == 0) tmisc[0] = lsum / (float)cnt;
+#pragma unroll
+                for (int c = 0; c < 4 * C4; ++c) {
+                    float g = z[c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                    if (lane == 0 && c < C) tg[N1 + N1 * C + c] = g;
+                }
             }
             group_bar(1);
-            // ---- backward of the tail: gW2, gb2, dPre (and gb1 from its column sums)
-            float *gb1 = tg, *gW2 = tg + N1, *gb2 = tg + N1 + N1 * C;
-            if (ttid == 0) {
-                float l = 0.f;
-                for (int s = 0; s < cnt; ++s) l += lb[s];
-                tmisc[0] = l / (float)cnt;
-            }
-            for (int i = ttid; i < N1 * C; i += 128) {
-                const int jj = i / C, c = i - jj * C;
-                float g = 0.f;
-                for (int s = 0; s < cnt; ++s) g = fmaf(Hb[s * N1 + jj], Z[s * Zs + c], g);
-                gW2[i] = g;
-            }
-            if (ttid < C) {
-                float g = 0.f;
-                for (int s = 0; s < cnt; ++s) g += Z[s * Zs + ttid];
-                gb2[ttid] = g;
+            // ---- backward of the tail.  gW2[j][c] = sum_s H[s][j] dZ[s][c]: thread = hidden unit j x half of the classes
+            {
+                const int jj = ttid & 63, half = ttid >> 6;
+                constexpr int G0 = (C4 + 1) / 2;          // float4 class groups of the first half; the second has C4 - G0
+                const int g_first = half * G0, g_count = half ? C4 - G0 : G0;
+                float g[4 * G0];
+#pragma unroll
+                for (int c = 0; c < 4 * G0; ++c) g[c] = 0.f;
+                for (int s = 0; s < cnt; ++s) {
+                    const float h = HT[jj * HS + s];
+#pragma unroll
+                    for (int c4 = 0; c4 < G0; ++c4) {
+                        if (c4 < g_count) {
+                            const float4 z = *reinterpret_cast<const float4 *>(dZ + s * CMAX + 4 * (g_first + c4));
+                            g[4 * c4] = fmaf(h, z.x, g[4 * c4]); g[4 * c4 + 1] = fmaf(h, z.y, g[4 * c4 + 1]);
+                            g[4 * c4 + 2] = fmaf(h, z.z, g[4 * c4 + 2]); g[4 * c4 + 3] = fmaf(h, z.w, g[4 * c4 + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4 * G0; ++c) {
+                    const int cls = 4 * g_first + c;
+                    if (c < 4 * g_count && cls < C) tg[N1 + jj * C + cls] = g[c];
+                }
             }
             if (k >= 1) mbar_wait(&bars.dpre_free, (k - 1) & 1, 10, dbg);   // backward MMAs of the previous env have read dPre
-            {
+            {   // dPre[s][j] = relu'(H[s][j]) sum_c dZ[s][c] W2[j][c]: thread = hidden unit j x 16 samples; W2 row in registers
                 const int jj = ttid & 63, sg = ttid >> 6;
-                float w2r[CMAX];
+                float w2r[4 * C4];
 #pragma unroll
-                for (int c = 0; c < CMAX; ++c) w2r[c] = c < C ? W2[jj * C + c] : 0.f;
+                for (int c4 = 0; c4 < C4; ++c4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(W2p + jj * CMAX + 4 * c4);
+                    w2r[4 * c4] = w.x; w2r[4 * c4 + 1] = w.y; w2r[4 * c4 + 2] = w.z; w2r[4 * c4 + 3] = w.w;
+                }
                 float colsum = 0.f;
                 const uint32_t cbase = (uint32_t)((jj >> 5) * 4096 + ((jj & 7) << 2));
                 const int q32 = (jj & 31) >> 3;
@@ -420,11 +447,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                 for (int i = 0; i < 16; ++i) {
                     const int s = sg * 16 + i;
                     float v = 0.f;
-                    if (s < cnt && Hb[s * N1 + jj] > 0.f) {
 #pragma unroll
-                        for (int c = 0; c < CMAX; ++c)
-                            if (c < C) v = fmaf(Z[s * Zs + c], w2r[c], v);
+                    for (int c4 = 0; c4 < C4; ++c4) {     // padded classes hold zeros in dZ and W2p
+                        const float4 z = *reinterpret_cast<const float4 *>(dZ + s * CMAX + 4 * c4);
+                        v = fmaf(z.x, w2r[4 * c4], v); v = fmaf(z.y, w2r[4 * c4 + 1], v);
+                        v = fmaf(z.z, w2r[4 * c4 + 2], v); v = fmaf(z.w, w2r[4 * c4 + 3], v);
                     }
+                    v = HT[jj * HS + s] > 0.f ? v : 0.f;  // rows beyond the minibatch have H = 0
                     colsum += v;
                     const uint32_t off = cbase + (uint32_t)(s * 128) + (uint32_t)((q32 ^ (s & 3)) << 5);
                     *reinterpret_cast<float *>(dP + off) = v;
@@ -435,7 +464,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             fence_async();
             group_bar(1);
             if (ttid == 0) mbar_arrive(&bars.dpre_ready);
-            if (ttid < N1) gb1[ttid] = gp[ttid] + gp[N1 + ttid];
+            if (q == 0) TC2_TRACE(5, 2 * k + 1);
+            if (ttid < N1) tg[ttid] = gp[ttid] + gp[N1 + ttid];          // gb1
             group_bar(1);
             // ---- tail gradient to HBM
             float gsum = 0.f;
@@ -459,14 +489,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             }
             group_bar(1);                                 // scratch is reused by the next env
         }
-    } else if (warp < 12) {
+    } else if (warp >= 8 && warp < 12) {
         // ===================== drain group (128 threads, named barrier 2): gradient tiles -> HBM
         const int q = warp - 8, dtid = tid - 256;
         unsigned char *stg = sm + OFF_G + q * 4096;
         uint32_t itG = 0;
         int k = 0;
         for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
-            float *gout = d.gnext + (size_t)e * d.Pp;
             float gsum = 0.f;
             for (int t = 0; t < TB; ++t, ++itG) {
                 const int g = itG & 1;
@@ -477,32 +506,36 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float v[32];
-                    {
-                        uint32_t v0[32], v1[32];
-                        TC2_LD32(taddr + 64 + 32 * h, v1);            // x . dPre_lo
-                        TC2_LD32(taddr + 32 * h, v0);                 // x . dPre_hi
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {            // 16 columns at a time keeps the warp under 80 registers
+                        uint32_t v0[16], v1[16];
+                        TC2_LD16(taddr + 64 + 32 * h + 16 * half, v1);        // x . dPre_lo
+                        TC2_LD16(taddr + 32 * h + 16 * half, v0);             // x . dPre_hi
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(v1[i]) + __uint_as_float(v0[i]);
+                        for (int i = 0; i < 16; ++i) v[16 * half + i] = __uint_as_float(v1[i]) + __uint_as_float(v0[i]);
                     }
                     if (h == 1) {                                     // accumulator drained: the next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.g_free[g]);
+                        if (q == 0) TC2_TRACE(6, itG);
                     }
-                    // lane = feature row; transpose through the warp's staging block so that stores are full lines
+                    // lane = feature row: the 32 x 32 block goes through the warp's staging block (128-byte
+                    // rows, SWIZZLE_128B) and leaves as ONE bulk tensor store; rows beyond D are clipped
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous block has left the staging block
                     __syncwarp();
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         *reinterpret_cast<float4 *>(stg + lane * 128 + swz16(c, lane)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                         gsum += (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
                     }
+                    fence_async();
                     __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + (lane >> 3), c = lane & 7;
-                        const float4 o = *reinterpret_cast<const float4 *>(stg + r * 128 + swz16(c, r));
-                        if (f0 + r < D) *reinterpret_cast<float4 *>(gout + (size_t)(f0 + r) * N1 + 32 * h + 4 * c) = o;
+                    if (lane == 0 && f0 < D) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                     ::"l"(gsel ? &map_g1 : &map_g0), "r"(32 * h), "r"(f0), "r"(e), "r"(smem_u32(stg)) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
             }
@@ -529,48 +562,120 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             }
             group_bar(2);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last gradient blocks have reached memory
     } else {
-        // ===================== converters (128 threads): lo parts of the landed tiles
-        const int ctid = tid - 384;
-        uint32_t itF = 0, itB = 0;
-        auto convert_b = [&]() {
-            for (int t = 0; t < TB; ++t, ++itB) {
-                const int s = itB % SB;
-                mbar_wait(&bars.fullB[s], (itB / SB) & 1, 13, dbg);
-                unsigned char *base = sm + OFF_B + s * B_STAGE;
+        // ===================== converters.  Warps 12-19 serve the forward ring: lo parts of the W1 tile the
+        // copy engine delivered, and the minibatch rows of the unit, which these threads load themselves
+        // (L2 hits: the rows are requested one env ahead) two units in advance into a register, then
+        // store as hi (raw) and lo -- one float4 per thread and unit, no gather warp, no cp.async.
+        // Warps 2, 20-22 do the same for the backward tiles (rows re-read from L2).  Many threads with
+        // little work each: what counts is the latency of a unit, not the throughput.
+        if (warp >= 12 && warp < 12 + CONV_F_WARPS) {
+            const int cid = tid - 384;                    // 0..255
+            // minibatch rows: sample cid >> 3, 16-byte chunk cid & 7 of the unit's 128 bytes (K-major, SWIZZLE_128B)
+            const int smp = cid >> 3, q = cid & 7;
+            const uint32_t xoff = (uint32_t)(smp * 128) + swz16(q, smp);
+            // W1 tile [32 f][64 j]: chunks c = cid and cid + 256 of [32 rows][16 chunks]: rows r and r + 16, chunk
+            // wq of the 256-byte row -> column half wq >> 3 (MN-major block), 32-byte chunks ^ (row & 3)
+            const int wr = cid >> 4, wq = cid & 15;
+            const uint32_t woff = (uint32_t)((wq >> 3) * 4096 + wr * 128) + swz32(wq & 7, wr);      // row + 16 has the same swizzle phase
+            auto fetch_row = [&](int e) {                 // two dependent global loads: fetched one env ahead
+                if (e >= e_end) return -1;
+                const int *idx; int cnt;
+                current_batch(d, a, e, d.sc + e, idx, cnt);
+                return smp < cnt ? idx[smp] : -1;
+            };
+            struct Unit { float4 w0, w1, x; };
+            auto load_unit = [&](int e, int row, int u) {       // everything this thread contributes to unit u of env e
+                Unit r;
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float *wt = d.w + (size_t)e * d.Pp + (size_t)(32 * u + wr) * N1 + 4 * wq;
+                r.w0 = 32 * u + wr < D ? __ldg(reinterpret_cast<const float4 *>(wt)) : zero4;
+                r.w1 = 32 * u + wr + 16 < D ? __ldg(reinterpret_cast<const float4 *>(wt + 16 * N1)) : zero4;
+                r.x = (row >= 0 && 32 * u + 4 * q < D) ? __ldg(reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + 32 * u + 4 * q)) : zero4;
+                return r;
+            };
+            constexpr int LA = 3;                         // units in flight in registers: 3 x 48 bytes x 256 threads = 36 KB
+            uint32_t itF = 0;
+            const int e0 = a.e_begin + blockIdx.x;
+            int row = fetch_row(e0);
+            Unit pend[LA];
+#pragma unroll
+            for (int i = 0; i < LA; ++i) pend[i] = e0 < e_end ? load_unit(e0, row, i) : Unit();
+            for (int e = e0; e < e_end; e += gridDim.x) {
+                const int next_row = fetch_row(e + gridDim.x);
+                for (int u = 0; u < UF; ++u, ++itF) {
+                    const int s = itF % SF;
+                    if (u == 8 && q == 0 && next_row >= 0) prefetch_l2(d.X + (size_t)next_row * d.Dp, D * 4);   // the next env's rows into L2
+                    mbar_wait(&bars.emptyF[s], ((itF / SF) & 1) ^ 1, 2, dbg);      // the MMAs that read this stage are done
+                    if (warp == 12) TC2_TRACE(1, itF);
+                    unsigned char *base = sm + OFF_F + s * F_STAGE;
+                    const Unit cur = pend[0];
+                    *reinterpret_cast<float4 *>(base + F_W + woff) = cur.w0;
+                    *reinterpret_cast<float4 *>(base + F_W + woff + 2048) = cur.w1;
+                    *reinterpret_cast<float4 *>(base + F_X + xoff) = cur.x;
+                    *reinterpret_cast<float4 *>(base + F_WLO + woff) = lo_of4(cur.w0);
+                    *reinterpret_cast<float4 *>(base + F_WLO + woff + 2048) = lo_of4(cur.w1);
+                    *reinterpret_cast<float4 *>(base + F_XLO + xoff) = lo_of4(cur.x);
+                    fence_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.convF[s]);
+                    if (warp == 12) TC2_TRACE(2, itF);
+                    // shift the window and request the unit LA ahead (it may belong to the next env)
+#pragma unroll
+                    for (int i = 0; i + 1 < LA; ++i) pend[i] = pend[i + 1];
+                    if (u + LA < UF) pend[LA - 1] = load_unit(e, row, u + LA);
+                    else if (e + (int)gridDim.x < e_end) pend[LA - 1] = load_unit(e + gridDim.x, next_row, u + LA - UF);
+                }
+                row = next_row;
+            }
+        } else if (warp == 2 || warp >= 12 + CONV_F_WARPS) {
+            const int bid = (warp == 2 ? 0 : warp - (11 + CONV_F_WARPS)) * 32 + lane;   // 0..127: sample bid >> 2, chunks bid & 3 and + 4
+            const int smp = bid >> 2, q2 = bid & 3;
+            uint32_t xoff[2];
+            xoff[0] = (uint32_t)(smp * 128) + swz32(q2, smp);
+            xoff[1] = (uint32_t)(smp * 128) + swz32(q2 + 4, smp);
+            auto fetch_row = [&](int e) {
+                if (e >= e_end) return -1;
+                const int *idx; int cnt;
+                current_batch(d, a, e, d.sc + e, idx, cnt);
+                return smp < cnt ? idx[smp] : -1;
+            };
+            float4 v[8];
+            auto load_tile = [&](int row, int t) {        // [4 blocks][2 chunks] of the sample's features [128t, 128t + 128)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int off = (i * 128 + ctid) * 16;
-                    *reinterpret_cast<float4 *>(base + B_XLO + off) = lo_of4(*reinterpret_cast<const float4 *>(base + off));
+                    const int f = 128 * t + 32 * (i >> 1) + 4 * (q2 + 4 * (i & 1));
+                    v[i] = (row >= 0 && f < D) ? __ldg(reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + f))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                fence_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.convB[s]);
-            }
-        };
-        int k = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
-            for (int u = 0; u < UF; ++u, ++itF) {
-                const int s = itF % SF;
-                mbar_wait(&bars.fullF[s], (itF / SF) & 1, 14, dbg);
-                unsigned char *base = sm + OFF_F + s * F_STAGE;
+            };
+            uint32_t itB = 0;
+            int row = fetch_row(a.e_begin + blockIdx.x);
+            if (a.e_begin + (int)blockIdx.x < e_end) load_tile(row, 0);
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+                const int next_row = fetch_row(e + gridDim.x);
+                for (int t = 0; t < TB; ++t, ++itB) {
+                    const int s = itB % SB;
+                    mbar_wait(&bars.emptyB[s], ((itB / SB) & 1) ^ 1, 3, dbg);
+                    unsigned char *base = sm + OFF_B + s * B_STAGE;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int off = (i * 128 + ctid) * 16;
-                    *reinterpret_cast<float4 *>(base + F_WLO + off) = lo_of4(*reinterpret_cast<const float4 *>(base + F_W + off));
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t off = (uint32_t)(4096 * (i >> 1)) + xoff[i & 1];
+                        *reinterpret_cast<float4 *>(base + off) = v[i];
+                        *reinterpret_cast<float4 *>(base + B_XLO + off) = lo_of4(v[i]);
+                    }
+                    fence_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.convB[s]);
+                    if (warp == 2) TC2_TRACE(7, itB);
+                    // the next tile's rows travel while this one is multiplied and drained
+                    if (t + 1 < TB) load_tile(row, t + 1);
+                    else if (e + (int)gridDim.x < e_end) load_tile(next_row, 0);
                 }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int off = (i * 128 + ctid) * 16;
-                    *reinterpret_cast<float4 *>(base + F_XLO + off) = lo_of4(*reinterpret_cast<const float4 *>(base + F_X + off));
-                }
-                fence_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.convF[s]);
+                row = next_row;
             }
-            if (k >= 1) convert_b();
         }
-        if (k >= 1) convert_b();
     }
     tc_fence_before();
     __syncthreads();
@@ -581,33 +686,120 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
 }  // namespace
 
 // ---------------------------------------------------------------- host side
+struct b2e_tc2_ctx {
+    CUtensorMap map_g[2];            // the two gradient buffers (they swap roles every step), same geometry
+    const float *g_base[2];
+    int pf_units;                    // B2E_TC_PF=0 switches the L2 prefetch of the next env's parameters off
+    int *dbg;                        // 16 watchdog ints, then 8 x 512 trace slots (long long)
+    int grid;
+    std::string trace_path;
+};
+
 bool b2e_tc2_supported(const void *dev) {
     const Dev &d = *static_cast<const Dev *>(dev);
     return d.kind == B2E_PROBLEM_SOFTMAX && d.hidden && !d.generic && d.N1 == tc2::N1 && d.B == tc2::B &&
            d.C >= 1 && d.C <= tc2::CMAX && d.D >= 32 && d.D % 4 == 0 && d.Dp == d.D && d.Pp % 4 == 0;
 }
 
-size_t b2e_tc2_smem_bytes() { return (size_t)tc2::SMEM_BYTES; }
+namespace {
+template <bool SECOND, int CC>
+bool tc2_set_smem() {
+    return cudaFuncSetAttribute(tc2::tc2_eval_kernel<SECOND, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) == cudaSuccess;
+}
+}  // namespace
 
-const char *b2e_tc2_prepare() {
-    const void *fns[] = {(const void *)tc2::tc2_eval_kernel<false, 10>, (const void *)tc2::tc2_eval_kernel<true, 10>,
-                         (const void *)tc2::tc2_eval_kernel<false, 0>, (const void *)tc2::tc2_eval_kernel<true, 0>};
-    for (const void *fn : fns)
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES) != cudaSuccess)
-            return "tcgen05 eval kernel does not fit shared memory";
-    return nullptr;
+b2e_tc2_ctx *b2e_tc2_create(const void *dev, int num_sms, std::string *error) {
+    const Dev &d = *static_cast<const Dev *>(dev);
+    if (!(tc2_set_smem<false, 10>() && tc2_set_smem<true, 10>() && tc2_set_smem<false, 0>() && tc2_set_smem<true, 0>())) {
+        *error = "tcgen05 eval kernel does not fit shared memory";
+        return nullptr;
+    }
+    b2e_tc2_ctx *ctx = new (std::nothrow) b2e_tc2_ctx();
+    if (!ctx) { *error = "out of host memory"; return nullptr; }
+    ctx->grid = d.E < num_sms ? d.E : num_sms;
+    ctx->dbg = nullptr;
+    if (cudaMalloc((void **)&ctx->dbg, tc2::DBG_BYTES) != cudaSuccess || cudaMemset(ctx->dbg, 0, tc2::DBG_BYTES) != cudaSuccess) {
+        *error = "cudaMalloc of the watchdog word failed";
+        delete ctx;
+        return nullptr;
+    }
+    if (const char *tp = getenv("B2E_TC_TRACE")) {
+        ctx->trace_path = tp;
+        const int one = 1;
+        cudaMemcpy(ctx->dbg + 15, &one, sizeof(int), cudaMemcpyHostToDevice);
+    }
+    // gradient blocks leave as bulk tensor stores: [E][D][64] fp32 tensors over the two gradient buffers, box {32, 32, 1}
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+        *error = "cuTensorMapEncodeTiled is not available in this driver";
+        b2e_tc2_destroy(ctx);
+        return nullptr;
+    }
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    const cuuint64_t dims[3] = {(cuuint64_t)tc2::N1, (cuuint64_t)d.D, (cuuint64_t)d.E};
+    const cuuint64_t strides[2] = {(cuuint64_t)tc2::N1 * 4, (cuuint64_t)d.Pp * 4};
+    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    auto encode = [&](CUtensorMap *map, const float *base, CUtensorMapSwizzle swizzle) {
+        return reinterpret_cast<encode_fn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    ctx->g_base[0] = d.gnext;
+    ctx->g_base[1] = d.gprev;
+    if (!encode(&ctx->map_g[0], d.gnext, CU_TENSOR_MAP_SWIZZLE_128B) ||
+        !encode(&ctx->map_g[1], d.gprev, CU_TENSOR_MAP_SWIZZLE_128B)) {
+        *error = "cuTensorMapEncodeTiled failed";
+        b2e_tc2_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
 }
 
-int b2e_tc2_launch(const void *dev, const void *args, int second, int grid, int *dbg, void *stream) {
+void b2e_tc2_destroy(b2e_tc2_ctx *ctx) {
+    if (!ctx) return;
+    if (!ctx->trace_path.empty()) {                      // timeline of CTA 0 in the last launch
+        static long long host[8 * 512];
+        if (cudaDeviceSynchronize() == cudaSuccess &&
+            cudaMemcpy(host, ctx->dbg + 16, sizeof(host), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE *fh = fopen(ctx->trace_path.c_str(), "w")) {
+                const char *names[8] = {"w_issue", "w_landed", "conv_f", "mma_f", "mma_b", "tail", "drain", "xb_issue"};
+                for (int r = 0; r < 8; ++r) {
+                    fprintf(fh, "%s", names[r]);
+                    for (int i = 0; i < 512 && host[r * 512 + i]; ++i) fprintf(fh, " %lld", host[r * 512 + i]);
+                    fprintf(fh, "\n");
+                }
+                fclose(fh);
+            }
+        }
+    }
+    cudaFree(ctx->dbg);
+    delete ctx;
+}
+
+int b2e_tc2_grid(const b2e_tc2_ctx *ctx) { return ctx->grid; }
+
+int b2e_tc2_watchdog(const b2e_tc2_ctx *ctx, int out[4]) {
+    return cudaMemcpy(out, ctx->dbg, 4 * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+
+int b2e_tc2_launch(const b2e_tc2_ctx *ctx, const void *dev, const void *args, int second, void *stream) {
     const Dev &d = *static_cast<const Dev *>(dev);
     const StepArgs &a = *static_cast<const StepArgs *>(args);
     const cudaStream_t cs = (cudaStream_t)stream;
+    const int grid = ctx->grid;
+    const int gsel = d.gnext == ctx->g_base[0] ? 0 : 1;
+    if (d.gnext != ctx->g_base[gsel]) return 1;          // not one of the two gradient buffers
+    const CUtensorMap &m0 = ctx->map_g[0], &m1 = ctx->map_g[1];
     if (d.C == 10) {
-        if (second) tc2::tc2_eval_kernel<true, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, dbg);
-        else tc2::tc2_eval_kernel<false, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, dbg);
+        if (second) tc2::tc2_eval_kernel<true, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        else tc2::tc2_eval_kernel<false, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
     } else {
-        if (second) tc2::tc2_eval_kernel<true, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, dbg);
-        else tc2::tc2_eval_kernel<false, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, dbg);
+        if (second) tc2::tc2_eval_kernel<true, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        else tc2::tc2_eval_kernel<false, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

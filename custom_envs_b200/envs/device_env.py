@@ -47,9 +47,10 @@ class DeviceEnvFront(BaseMultiEnvironment):
                     action_version=self.version.action, reward_version=self.version.reward)
 
     def fuse_key(self):
-        feats, targs = self.model.device_arrays()
-        data = None if feats is None else (tuple(feats.shape), float(feats.sum()), float(targs.sum()))
-        return (type(self).__name__, self.model.spec, data, tuple(sorted(self.backend_kwargs().items())))
+        """Envs with equal keys can live in one ``BatchedOptEnv``: same env class, problem shape,
+        versions and the same data-set CONTENT (a digest, computed once per data-set object)."""
+        return (type(self).__name__, self.model.spec, self.model.data_key(),
+                tuple(sorted(self.backend_kwargs().items())))
 
     def seed(self, seed=None):
         super().seed(seed)

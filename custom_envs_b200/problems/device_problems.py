@@ -26,6 +26,9 @@ class _DeviceProblem(BaseProblem):
         """(features float32 [N,D], targets) as the kernel wants them, or (None, None)."""
         return None, None
 
+    def data_key(self):
+        return None
+
     @property
     def batch_size(self):
         return None
@@ -125,6 +128,25 @@ class OptimizeNN(_DeviceProblem):
 
     def device_arrays(self):
         return self._features, self._labels
+
+    def data_key(self):
+        """Content digest of (features, labels): envs may share one data-set replica in HBM only if
+        their arrays are EQUAL, not merely of equal shape and sum.  Computed once per data-set
+        object and cached on it, so thousands of envs over one data set hash it once."""
+        cached = getattr(self.data_set, '_b2e_digest', None)
+        if cached is None:
+            import hashlib
+            digest = hashlib.blake2b(digest_size=16)
+            for array in (self._features, self._labels):
+                host = array.detach().cpu().numpy() if hasattr(array, 'detach') else np.asarray(array)
+                digest.update(str((host.shape, host.dtype.str)).encode())
+                digest.update(np.ascontiguousarray(host).tobytes())
+            cached = digest.hexdigest()
+            try:
+                self.data_set._b2e_digest = cached
+            except AttributeError:          # data-set type without a __dict__: recompute next time
+                pass
+        return cached
 
     @property
     def batch_size(self):

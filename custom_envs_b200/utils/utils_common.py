@@ -59,7 +59,9 @@ class History(Mapping):
         return '<History<max_history={}, shapes={!r}>>'.format(self.max_history, self.shapes)
 
     def __getitem__(self, key):
-        return self._data[key].copy()
+        # entries keep the dtype they were appended with (TensorFlow hands the env float32 losses):
+        # the stacked array is float32 once every entry is, float64 while initial zeros remain
+        return np.asarray(self._data[key])
 
     def __iter__(self):
         return iter(self.shapes)
@@ -68,15 +70,14 @@ class History(Mapping):
         return len(self.shapes)
 
     def reset_with_value(self, value):
-        self._data = {name: np.full((self.max_history,) + shape, value, np.float64)
+        self._data = {name: [np.full(shape, value, np.float64)] * self.max_history
                       for name, shape in self.shapes.items()}
         self.iteration = 0
 
     def reset(self, **named_items):
         if named_items:
             assert self.keys() == named_items.keys()
-            self._data = {name: np.repeat(np.reshape(np.asarray(item, np.float64), (1,) + self.shapes[name]),
-                                          self.max_history, axis=0)
+            self._data = {name: [np.reshape(item, self.shapes[name])] * self.max_history
                           for name, item in named_items.items()}
             self.iteration = 0
         else:
@@ -85,15 +86,13 @@ class History(Mapping):
     def append(self, **named_items):
         assert self.keys() == named_items.keys()
         for name, item in named_items.items():
-            buf = self._data[name]
-            buf[1:] = buf[:-1].copy()
-            buf[0] = np.reshape(item, self.shapes[name])
+            self._data[name] = [np.reshape(item, self.shapes[name])] + self._data[name][:-1]   # newest first
         self.iteration = (self.iteration + 1) % self.max_history
 
     def build_multistate(self):
         """One tuple per agent: for each key (insertion order) its ``depth`` newest-first
         values; single-element keys are broadcast to every agent."""
-        blocks = [self._data[name].reshape(self.max_history, -1) for name in self.shapes]
+        blocks = [self[name].reshape(self.max_history, -1) for name in self.shapes]
         width = max(block.shape[1] for block in blocks)
         rows = np.concatenate([np.broadcast_to(block, (self.max_history, width)) if block.shape[1] == 1
                                else block for block in blocks], axis=0)

@@ -331,3 +331,22 @@ def test_policy_actions_chunks_and_clips():
     assert mean.shape == value.shape == (101,)
     gen = torch.Generator().manual_seed(1)
     assert policy.act(obs, generator=gen).shape == (101,)
+
+
+def test_fuse_key_is_the_data_content_not_its_shape_and_sums():
+    """Envs are fused onto one HBM replica of a data set only if their arrays are EQUAL: the same
+    rows in another order (equal shape, equal sums) must not share the first env's arrays."""
+    from custom_envs_b200.compat import make
+    import custom_envs  # noqa: F401  (registers the env ids)
+    from custom_envs_b200.dataset.inmemorydataset import InMemoryDataSet
+    rng = np.random.RandomState(0)
+    feats = rng.uniform(size=(40, 4))
+    targs = np.eye(3)[np.arange(40) % 3]
+    data_sets = [InMemoryDataSet(feats, targs, 8), InMemoryDataSet(feats[::-1].copy(), targs[::-1].copy(), 8),
+                 InMemoryDataSet(feats.copy(), targs.copy(), 8)]
+    envs = [make('MultiOptLRs-v0', problem='nn', problem_kwargs=dict(layers=(), data_set=data))
+            for data in data_sets + data_sets[:1]]
+    keys = [getattr(env, 'unwrapped', env).fuse_key() for env in envs]
+    assert keys[0] != keys[1]                      # permuted rows: not the same data
+    assert keys[0] == keys[2] == keys[3]           # equal content / the same object: fusable
+    assert hasattr(data_sets[0], '_b2e_digest')    # hashed once per data-set object
