@@ -11,16 +11,16 @@
 // lo parts are one-sided and their product is not negligible).
 //
 // Persistent, one 768-thread CTA per SM, warp-specialised; envs e = blockIdx.x + k * gridDim.x:
-//   warp 0      L2 prefetcher : the next env's parameters, one env ahead of the forward stream
-//   warp 1      (spare)
+//   warp 0      W producer  : W1 tile [32 f][64 j] of the forward unit -> stage, one bulk tensor copy; L2
+//                             prefetch of the next env's parameters
+//   warp 1      XF producer : minibatch rows [32 s][32 f] of the forward unit (gather), 16-byte cp.async
+//   warp 2      XB producer : minibatch rows [32 s][128 f] of a backward tile (L2 hits), 16-byte cp.async
 //   warps 3, 23 MMA issuers : forward units / backward tiles, one elected lane each, two independent
 //                             in-order queues; the tail of env k runs under the forward stream of env k+1
 //   warps 4-7   tail        : TMEM -> Hpre, bias/relu/layer 2/softmax-CE/backward -> dPre operand
 //   warps 8-11  drain       : gradient tiles TMEM -> registers -> shared-memory transpose -> HBM;
 //                             second eval: the step's scalars (reward, done, info, cursor)
-//   warps 12-19 forward converters : lo part of the landed W1 tile; the unit's minibatch rows [32 s][32 f] are
-//                             loaded by these threads (L2 -> register, two units ahead) and stored as hi + lo
-//   warps 2, 20-22 backward converters : rows [32 s][128 f] of a backward tile, L2 -> register -> hi + lo
+//   warps 12-22 converters  : lo parts of every landed operand tile (12-19 forward ring, 20-22 backward ring)
 // Pipelines: forward ring (4 stages x 24 KB: W hi/lo, X hi/lo), backward ring (2 x 32 KB: X hi/lo),
 // both full -> converted -> (tcgen05.commit) empty; TMEM: four forward accumulators [128 x 64] (every
 // fourth unit each: the tensor core's adder truncates, so long sums are split and added by threads) and
@@ -65,13 +65,13 @@ constexpr int SMEM_BYTES = OFF_TAIL + T_END * 4 + 1024;   // + slack to align th
 constexpr int TMEM_COLS = 512;                        // forward 4 x 64, gradient 2 x 128 columns
 constexpr int TM_F = 0, TM_G = 256, NACC = 4;
 constexpr int THREADS = 768;                          // 24 warps, at most 80 registers each
-constexpr int CONV_F_WARPS = 8, CONV_B_WARPS = 4, MMA_B_WARP = 23;   // backward converters: warps 2, 20, 21, 22
+constexpr int CONV_F_WARPS = 8, CONV_B_WARPS = 3, MMA_B_WARP = 23;
 constexpr int DBG_BYTES = 64 + 8 * 512 * 8;
 constexpr long long WATCHDOG_CYCLES = 1500000000LL;   // ~0.8 s: a wait this long is a protocol bug
 
 struct Bars {
-    uint64_t convF[SF], emptyF[SF];
-    uint64_t convB[SB], emptyB[SB];
+    uint64_t fullF[SF], convF[SF], emptyF[SF];
+    uint64_t fullB[SB], convB[SB], emptyB[SB];
     uint64_t g_full[2], g_free[2], tail_done[2];
     uint64_t fwd_done, fwd_free, dpre_ready, dpre_free;
 };
@@ -104,6 +104,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int co
 }
 __device__ __forceinline__ void prefetch_l2(const void *src, int bytes) {              // bytes: multiple of 16
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {      // bytes < 16: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {       // arrive when this thread's copies have landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
@@ -157,7 +163,8 @@ __device__ __forceinline__ uint32_t swz16(int q, int r) { return (uint32_t)((q ^
 template <bool SECOND, int CC>
 __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_constant__ Dev d,
                                                               const __grid_constant__ StepArgs a,
-                                                                                                                            const __grid_constant__ CUtensorMap map_g0,
+                                                              const __grid_constant__ CUtensorMap map_w,
+                                                              const __grid_constant__ CUtensorMap map_g0,
                                                               const __grid_constant__ CUtensorMap map_g1, int gsel, int pf_units, int *dbg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) Bars bars;
@@ -178,8 +185,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
 #define TC2_TRACE(role, n) do { if (trace && lane == 0 && (n) < 512) trace[(role) * 512 + (n)] = clock64(); } while (0)
 
     if (tid == 0) {
-        for (int s = 0; s < SF; ++s) { mbar_init(&bars.convF[s], CONV_F_WARPS); mbar_init(&bars.emptyF[s], 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(&bars.convB[s], CONV_B_WARPS); mbar_init(&bars.emptyB[s], 1); }
+        for (int s = 0; s < SF; ++s) { mbar_init(&bars.fullF[s], 33); mbar_init(&bars.convF[s], CONV_F_WARPS); mbar_init(&bars.emptyF[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&bars.fullB[s], 32); mbar_init(&bars.convB[s], CONV_B_WARPS); mbar_init(&bars.emptyB[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars.g_full[s], 1); mbar_init(&bars.g_free[s], 4); mbar_init(&bars.tail_done[s], 1);
         }
@@ -197,24 +204,100 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
-        // ===================== L2 prefetcher.  The forward operands reach shared memory through the
-        // converter threads' registers (this SM's copy engine retires one bulk tensor copy per ~360
-        // cycles whatever its size up to 4 KB -- profiles/tools/tma_rate_probe.cu -- which is a third
-        // of the rate the HBM share of an SM needs), so the bytes in flight are bounded by registers and
-        // the loads must be L2 hits: this warp requests W1 and the tail parameters of env k+1 while env
-        // k streams (203 KB per SM, 30 MB for the whole GPU, one env ahead).
+        // ===================== W producer.  This SM's copy engine retires one bulk tensor copy per
+        // ~400-600 cycles whatever its size up to 16 KB (profiles/tools/tma_rate_probe.cu), so the W1 tile
+        // of a unit travels as ONE copy: a 4-d view [E][2 column halves][D][32] of the parameter array
+        // (strides 256 B / 128 B / Pp*4) with box {32, 32, 2, 1} lands as the two MN-major blocks
+        // [half][32 f][128 B] of the stage, swizzle 128B_ATOM_32B; rows beyond D arrive as zeros.
+        // The next env's parameters are requested into L2 one env ahead.
         auto prefetch_env = [&](int e) {
             const char *base = reinterpret_cast<const char *>(d.w + (size_t)e * d.Pp);
             const int lines = (d.P * 4 + 127) >> 7;
             for (int i = lane; i < lines; i += 32)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
         };
-        int k = 0;
+        uint32_t it = 0;
         if (a.e_begin + (int)blockIdx.x < e_end && pf_units > 0) prefetch_env(a.e_begin + blockIdx.x);
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
             if (e + (int)gridDim.x < e_end && pf_units > 0) prefetch_env(e + gridDim.x);
-            mbar_wait(&bars.fwd_done, k & 1, 1, dbg);     // pace: one env ahead of the forward stream
+            for (int u = 0; u < UF; ++u, ++it) {
+                const int s = it % SF;
+                mbar_wait(&bars.emptyF[s], ((it / SF) & 1) ^ 1, 1, dbg);
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars.fullF[s])), "r"(8192u) : "memory");
+                    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                 ::"r"(sbase + OFF_F + s * F_STAGE + F_W), "l"(&map_w), "r"(0), "r"(32 * u), "r"(0), "r"(e),
+                                   "r"(smem_u32(&bars.fullF[s])) : "memory");
+                }
+                TC2_TRACE(0, it);
+            }
         }
+    } else if (warp == 1 || warp == 2) {
+        // ===================== X producers (gather of the minibatch rows, 16-byte cp.async that complete on
+        // the stage's mbarrier: of everything tried -- one bulk tensor copy per row piece (~250 cycles each),
+        // loads through the converters' registers -- this leaves the forward stream the least exposed):
+        // warp 1, forward unit u = features [32u, 32u + 32): sample sr = 4 i + (lane >> 3), chunk q = lane & 7,
+        //         K-major SWIZZLE_128B rows [32 s][128 B];
+        // warp 2, backward tile t = features [128t, 128t + 128): four 32-feature blocks of [32 s][128 B],
+        //         MN-major 128B_BASE32B (L2 hits: the forward pass read these rows microseconds ago).
+        // Per env the eight row pointers of a lane are fixed; per unit only a byte offset is added.
+        const bool fwd = warp == 1;
+        const int g8 = lane >> 3, q = lane & 7;
+        uint32_t lane_dst[2];                             // forward: the swizzle phase of row 4 i + g8 alternates with i
+        lane_dst[0] = (uint32_t)(g8 * 128) + (fwd ? swz16(q, g8) : swz32(q, g8));
+        lane_dst[1] = (uint32_t)(g8 * 128) + (fwd ? swz16(q, 4 + g8) : swz32(q, g8));
+        uint32_t it = 0;
+        // the row indices of an env sit behind two dependent global loads (cursor -> order -> row):
+        // they are fetched one env ahead, so that no env starts with that latency
+        auto fetch_row = [&](int e) {
+            if (e >= e_end) return -1;
+            const int *idx; int cnt;
+            current_batch(d, a, e, d.sc + e, idx, cnt);
+            return lane < cnt ? idx[lane] : -1;
+        };
+        int next_row = fetch_row(a.e_begin + blockIdx.x);
+        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+            const int my_row = next_row;
+            next_row = fetch_row(e + gridDim.x);          // consumed at unit 8 / at the next env: the loads have time to land
+            const char *rowp[8];
+            int rbytes[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = __shfl_sync(0xffffffffu, my_row, 4 * i + g8);
+                rowp[i] = reinterpret_cast<const char *>(d.X + (row >= 0 ? (size_t)row * d.Dp : 0)) + 16 * q;
+                rbytes[i] = row >= 0 ? 16 : 0;
+            }
+            if (fwd) {
+                for (int u = 0; u < UF; ++u, ++it) {
+                    const int s = it % SF;
+                    mbar_wait(&bars.emptyF[s], ((it / SF) & 1) ^ 1, 2, dbg);
+                    const uint32_t base = sbase + OFF_F + s * F_STAGE + F_X;
+                    const bool in = 32 * u + 4 * q < D;   // the last unit may be partial
+                    if (u == 8 && next_row >= 0) prefetch_l2(d.X + (size_t)next_row * d.Dp, D * 4);   // the next env's rows into L2
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        cp_async16(base + lane_dst[i & 1] + 512 * i, in ? rowp[i] + 128 * u : rowp[i], in ? rbytes[i] : 0);
+                    cp_async_arrive(&bars.fullF[s]);
+                }
+            } else {
+                for (int t = 0; t < TB; ++t, ++it) {
+                    const int s = it % SB;
+                    mbar_wait(&bars.emptyB[s], ((it / SB) & 1) ^ 1, 3, dbg);
+                    const uint32_t base = sbase + OFF_B + s * B_STAGE;
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk) {
+                        const bool in = 128 * t + 32 * blk + 4 * q < D;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            cp_async16(base + lane_dst[0] + 4096 * blk + 512 * i,
+                                       in ? rowp[i] + 512 * t + 128 * blk : rowp[i], in ? rbytes[i] : 0);
+                    }
+                    cp_async_arrive(&bars.fullB[s]);
+                    TC2_TRACE(7, it);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp == 3 || warp == MMA_B_WARP) {
         // ===================== MMA issuers: warp 3 the forward units, warp 23 the backward tiles.  Two
         // in-order queues with blocking waits; a backward tile that is not ready (dPre, accumulator
@@ -564,116 +647,58 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last gradient blocks have reached memory
     } else {
-        // ===================== converters.  Warps 12-19 serve the forward ring: lo parts of the W1 tile the
-        // copy engine delivered, and the minibatch rows of the unit, which these threads load themselves
-        // (L2 hits: the rows are requested one env ahead) two units in advance into a register, then
-        // store as hi (raw) and lo -- one float4 per thread and unit, no gather warp, no cp.async.
-        // Warps 2, 20-22 do the same for the backward tiles (rows re-read from L2).  Many threads with
-        // little work each: what counts is the latency of a unit, not the throughput.
+        // ===================== converters: lo parts of the landed tiles.  Warps 12-19 serve the forward
+        // ring, warps 20-22 the backward ring, so that neither queue waits for the other.  Many
+        // threads with a few float4 each: what counts is the latency of a unit, not the throughput
+        // (every microsecond a stage spends here is a microsecond it is not in flight to HBM).
         if (warp >= 12 && warp < 12 + CONV_F_WARPS) {
             const int cid = tid - 384;                    // 0..255
-            // minibatch rows: sample cid >> 3, 16-byte chunk cid & 7 of the unit's 128 bytes (K-major, SWIZZLE_128B)
-            const int smp = cid >> 3, q = cid & 7;
-            const uint32_t xoff = (uint32_t)(smp * 128) + swz16(q, smp);
-            // W1 tile [32 f][64 j]: chunks c = cid and cid + 256 of [32 rows][16 chunks]: rows r and r + 16, chunk
-            // wq of the 256-byte row -> column half wq >> 3 (MN-major block), 32-byte chunks ^ (row & 3)
-            const int wr = cid >> 4, wq = cid & 15;
-            const uint32_t woff = (uint32_t)((wq >> 3) * 4096 + wr * 128) + swz32(wq & 7, wr);      // row + 16 has the same swizzle phase
-            auto fetch_row = [&](int e) {                 // two dependent global loads: fetched one env ahead
-                if (e >= e_end) return -1;
-                const int *idx; int cnt;
-                current_batch(d, a, e, d.sc + e, idx, cnt);
-                return smp < cnt ? idx[smp] : -1;
-            };
-            struct Unit { float4 w0, w1, x; };
-            auto load_unit = [&](int e, int row, int u) {       // everything this thread contributes to unit u of env e
-                Unit r;
-                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float *wt = d.w + (size_t)e * d.Pp + (size_t)(32 * u + wr) * N1 + 4 * wq;
-                r.w0 = 32 * u + wr < D ? __ldg(reinterpret_cast<const float4 *>(wt)) : zero4;
-                r.w1 = 32 * u + wr + 16 < D ? __ldg(reinterpret_cast<const float4 *>(wt + 16 * N1)) : zero4;
-                r.x = (row >= 0 && 32 * u + 4 * q < D) ? __ldg(reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + 32 * u + 4 * q)) : zero4;
-                return r;
-            };
-            constexpr int LA = 3;                         // units in flight in registers: 3 x 48 bytes x 256 threads = 36 KB
             uint32_t itF = 0;
-            const int e0 = a.e_begin + blockIdx.x;
-            int row = fetch_row(e0);
-            Unit pend[LA];
-#pragma unroll
-            for (int i = 0; i < LA; ++i) pend[i] = e0 < e_end ? load_unit(e0, row, i) : Unit();
-            for (int e = e0; e < e_end; e += gridDim.x) {
-                const int next_row = fetch_row(e + gridDim.x);
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
                 for (int u = 0; u < UF; ++u, ++itF) {
                     const int s = itF % SF;
-                    if (u == 8 && q == 0 && next_row >= 0) prefetch_l2(d.X + (size_t)next_row * d.Dp, D * 4);   // the next env's rows into L2
-                    mbar_wait(&bars.emptyF[s], ((itF / SF) & 1) ^ 1, 2, dbg);      // the MMAs that read this stage are done
+                    mbar_wait(&bars.fullF[s], (itF / SF) & 1, 14, dbg);
                     if (warp == 12) TC2_TRACE(1, itF);
                     unsigned char *base = sm + OFF_F + s * F_STAGE;
-                    const Unit cur = pend[0];
-                    *reinterpret_cast<float4 *>(base + F_W + woff) = cur.w0;
-                    *reinterpret_cast<float4 *>(base + F_W + woff + 2048) = cur.w1;
-                    *reinterpret_cast<float4 *>(base + F_X + xoff) = cur.x;
-                    *reinterpret_cast<float4 *>(base + F_WLO + woff) = lo_of4(cur.w0);
-                    *reinterpret_cast<float4 *>(base + F_WLO + woff + 2048) = lo_of4(cur.w1);
-                    *reinterpret_cast<float4 *>(base + F_XLO + xoff) = lo_of4(cur.x);
+                    // loads first, stores after: the compiler cannot move a shared-memory load above an
+                    // earlier store to the same array
+                    float4 v[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {         // 512 float4 of W, then 256 of X
+                        const int c = i * 256 + cid;
+                        v[i] = *reinterpret_cast<const float4 *>(base + (i < 2 ? F_W + c * 16 : F_X + (c - 512) * 16));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = i * 256 + cid;
+                        *reinterpret_cast<float4 *>(base + (i < 2 ? F_WLO + c * 16 : F_XLO + (c - 512) * 16)) = lo_of4(v[i]);
+                    }
                     fence_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.convF[s]);
                     if (warp == 12) TC2_TRACE(2, itF);
-                    // shift the window and request the unit LA ahead (it may belong to the next env)
-#pragma unroll
-                    for (int i = 0; i + 1 < LA; ++i) pend[i] = pend[i + 1];
-                    if (u + LA < UF) pend[LA - 1] = load_unit(e, row, u + LA);
-                    else if (e + (int)gridDim.x < e_end) pend[LA - 1] = load_unit(e + gridDim.x, next_row, u + LA - UF);
                 }
-                row = next_row;
             }
-        } else if (warp == 2 || warp >= 12 + CONV_F_WARPS) {
-            const int bid = (warp == 2 ? 0 : warp - (11 + CONV_F_WARPS)) * 32 + lane;   // 0..127: sample bid >> 2, chunks bid & 3 and + 4
-            const int smp = bid >> 2, q2 = bid & 3;
-            uint32_t xoff[2];
-            xoff[0] = (uint32_t)(smp * 128) + swz32(q2, smp);
-            xoff[1] = (uint32_t)(smp * 128) + swz32(q2 + 4, smp);
-            auto fetch_row = [&](int e) {
-                if (e >= e_end) return -1;
-                const int *idx; int cnt;
-                current_batch(d, a, e, d.sc + e, idx, cnt);
-                return smp < cnt ? idx[smp] : -1;
-            };
-            float4 v[8];
-            auto load_tile = [&](int row, int t) {        // [4 blocks][2 chunks] of the sample's features [128t, 128t + 128)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int f = 128 * t + 32 * (i >> 1) + 4 * (q2 + 4 * (i & 1));
-                    v[i] = (row >= 0 && f < D) ? __ldg(reinterpret_cast<const float4 *>(d.X + (size_t)row * d.Dp + f))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
+        } else if (warp >= 12 + CONV_F_WARPS && warp < 12 + CONV_F_WARPS + CONV_B_WARPS) {
+            const int cid = tid - 384 - 32 * CONV_F_WARPS;   // 0..95
             uint32_t itB = 0;
-            int row = fetch_row(a.e_begin + blockIdx.x);
-            if (a.e_begin + (int)blockIdx.x < e_end) load_tile(row, 0);
             for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
-                const int next_row = fetch_row(e + gridDim.x);
                 for (int t = 0; t < TB; ++t, ++itB) {
                     const int s = itB % SB;
-                    mbar_wait(&bars.emptyB[s], ((itB / SB) & 1) ^ 1, 3, dbg);
+                    mbar_wait(&bars.fullB[s], (itB / SB) & 1, 13, dbg);
                     unsigned char *base = sm + OFF_B + s * B_STAGE;
+                    constexpr int CT = 32 * CONV_B_WARPS, PER = (1024 + CT - 1) / CT;     // 96 threads, 11 float4 each
+                    float4 v[PER];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint32_t off = (uint32_t)(4096 * (i >> 1)) + xoff[i & 1];
-                        *reinterpret_cast<float4 *>(base + off) = v[i];
-                        *reinterpret_cast<float4 *>(base + B_XLO + off) = lo_of4(v[i]);
-                    }
+                    for (int i = 0; i < PER; ++i)
+                        if (i * CT + cid < 1024) v[i] = *reinterpret_cast<const float4 *>(base + (i * CT + cid) * 16);
+#pragma unroll
+                    for (int i = 0; i < PER; ++i)
+                        if (i * CT + cid < 1024) *reinterpret_cast<float4 *>(base + B_XLO + (i * CT + cid) * 16) = lo_of4(v[i]);
                     fence_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars.convB[s]);
-                    if (warp == 2) TC2_TRACE(7, itB);
-                    // the next tile's rows travel while this one is multiplied and drained
-                    if (t + 1 < TB) load_tile(row, t + 1);
-                    else if (e + (int)gridDim.x < e_end) load_tile(next_row, 0);
                 }
-                row = next_row;
             }
         }
     }
@@ -687,7 +712,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
 
 // ---------------------------------------------------------------- host side
 struct b2e_tc2_ctx {
-    CUtensorMap map_g[2];            // the two gradient buffers (they swap roles every step), same geometry
+    CUtensorMap map_w;               // parameters as [E][2 column halves][D][32] fp32, box {32, 32, 2, 1}
+    CUtensorMap map_g[2];            // the two gradient buffers (they swap roles every step) as [E][D][64], box {32, 32, 1}
     const float *g_base[2];
     int pf_units;                    // B2E_TC_PF=0 switches the L2 prefetch of the next env's parameters off
     int *dbg;                        // 16 watchdog ints, then 8 x 512 trace slots (long long)
@@ -742,7 +768,7 @@ b2e_tc2_ctx *b2e_tc2_create(const void *dev, int num_sms, std::string *error) {
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     const cuuint64_t dims[3] = {(cuuint64_t)tc2::N1, (cuuint64_t)d.D, (cuuint64_t)d.E};
     const cuuint64_t strides[2] = {(cuuint64_t)tc2::N1 * 4, (cuuint64_t)d.Pp * 4};
-    const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {32, 32, 1}, estr[4] = {1, 1, 1, 1};
     auto encode = [&](CUtensorMap *map, const float *base, CUtensorMapSwizzle swizzle) {
         return reinterpret_cast<encode_fn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
                                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -750,7 +776,13 @@ b2e_tc2_ctx *b2e_tc2_create(const void *dev, int num_sms, std::string *error) {
     };
     ctx->g_base[0] = d.gnext;
     ctx->g_base[1] = d.gprev;
-    if (!encode(&ctx->map_g[0], d.gnext, CU_TENSOR_MAP_SWIZZLE_128B) ||
+    const cuuint64_t wdims[4] = {32, (cuuint64_t)d.D, 2, (cuuint64_t)d.E};
+    const cuuint64_t wstrides[3] = {(cuuint64_t)tc2::N1 * 4, 128, (cuuint64_t)d.Pp * 4};
+    const cuuint32_t wbox[4] = {32, 32, 2, 1};
+    if (reinterpret_cast<encode_fn>(fn)(&ctx->map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)d.w, wdims, wstrides, wbox, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        !encode(&ctx->map_g[0], d.gnext, CU_TENSOR_MAP_SWIZZLE_128B) ||
         !encode(&ctx->map_g[1], d.gprev, CU_TENSOR_MAP_SWIZZLE_128B)) {
         *error = "cuTensorMapEncodeTiled failed";
         b2e_tc2_destroy(ctx);
@@ -795,11 +827,11 @@ int b2e_tc2_launch(const b2e_tc2_ctx *ctx, const void *dev, const void *args, in
     if (d.gnext != ctx->g_base[gsel]) return 1;          // not one of the two gradient buffers
     const CUtensorMap &m0 = ctx->map_g[0], &m1 = ctx->map_g[1];
     if (d.C == 10) {
-        if (second) tc2::tc2_eval_kernel<true, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
-        else tc2::tc2_eval_kernel<false, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        if (second) tc2::tc2_eval_kernel<true, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, ctx->map_w, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        else tc2::tc2_eval_kernel<false, 10><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, ctx->map_w, m0, m1, gsel, ctx->pf_units, ctx->dbg);
     } else {
-        if (second) tc2::tc2_eval_kernel<true, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
-        else tc2::tc2_eval_kernel<false, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        if (second) tc2::tc2_eval_kernel<true, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, ctx->map_w, m0, m1, gsel, ctx->pf_units, ctx->dbg);
+        else tc2::tc2_eval_kernel<false, 0><<<grid, tc2::THREADS, tc2::SMEM_BYTES, cs>>>(d, a, ctx->map_w, m0, m1, gsel, ctx->pf_units, ctx->dbg);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
