@@ -3,23 +3,30 @@
 
     python bench.py --gpus N --steps K --warmup W          # the CUDA path (this repo)
     python bench.py --impl reference --gpus N ...          # the reference algorithm on host CPUs
+    python bench.py --envs-total E --gpus N ...            # strong scaling: E envs sharded over N GPUs
 
 Workload (N=1): BASELINE.json configs[3], the configuration the headline target is quoted
 on: MultiOptLRs, 2-layer MLP 784->64->10 on synthetic MNIST-shaped data (60000 rows),
 minibatch 32, max_history 5, 4096 lock-step envs per GPU (weak scaling: 4096 x N envs).
 One "step" = one batched env step over all envs = one b2e_step call (for this workload a
-pipeline of four kernels: eval, update, eval, observations + two tiny bookkeeping launches;
-three with B2E_FUSE_UPDATE=1, which applies the update in the first eval's epilogue).
+pipeline of four kernels: tcgen05 eval, update, tcgen05 eval, observations + two tiny
+bookkeeping launches).  The timed window contains one episode end of every env (the step
+counters are advanced so that all envs hit max_batches in the middle of the window and are
+re-initialised by the library's auto-reset, as the reference's workers do).
 
 Reported on one JSON line:
   value     env-steps/s with actions already in HBM (device API, CUDA events, max over ranks)
   e2e       the same metric through the reference-facing OptVecEnv.step() with HOST numpy
             buffers: H2D of the actions and D2H of observations/rewards/dones/infos inside
             the timed region
-  roofline  algorithmic bytes per launch (4*[P*(5H+3)+B*(D+1)] per env-step)
-            / average launch duration, against the measured HBM copy bandwidth
-  cpu_baseline  the oracle (numpy restatement of the reference) on the host cores, on a
-            bounded sample of the same workload
+  roofline  SURVEY 8d: algorithmic bytes of the whole step (4*[P*(5H+3)+B*(D+1)] per env-step)
+            / step time, against the measured HBM copy bandwidth; the per-kernel figures
+            (own algorithmic bytes / own CUDA-event duration) are listed beside it
+  parity    one more step after the timed loop, replayed by the oracle for six sampled envs
+            (first two, E/3, 2E/3, last two) from the device's own state
+  cpu_baseline  the oracle on the host cores, on a bounded sample of the same workload:
+            "port" = vectorised numpy (SURVEY 8d path ii), "faithful" = per-env Python
+            objects, thread per env over pipes (path i)
 """
 import argparse
 import contextlib
@@ -36,6 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, HID, C, BATCH, ROWS, HIST = 784, 64, 10, 32, 60000, 5
+MAX_BATCHES = 400                 # the envs' default episode length (envs/multioptlrs.py:39)
 NUM_PARAMS = D * HID + HID + HID * C + C
 BYTES_PER_ENV_STEP = 4 * (NUM_PARAMS * (5 * HIST + 3) + BATCH * (D + 1))      # 5 800 160
 WORKLOAD = 'MultiOptLRs MLP 784-64-10, B=32, H=5, 60000x784 synthetic rows'
@@ -133,12 +141,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU (oracle) arm
+CPU_ROWS = 4096          # data-set rows of the CPU arms (the minibatch stream touches 32 rows per env-step either way)
+
+
+def cpu_faithful(max_seconds=25.0):
+    """SURVEY 8d path (i): per-env Python objects (oracle/faithful_env.py), one thread per env
+    over pipes.  The per-agent Python work holds the GIL, so the rate does not grow with the
+    thread count; runs E_cpu in {1, min(cores, 4)} for as many steps as the time box allows."""
+    from oracle import faithful_env as fe
+    from oracle import optenv_oracle as orc
+    feats, labels = synthetic_data(CPU_ROWS)
+    spec = orc.ProblemSpec('softmax', D, (HID,), C)
+    cores = os.cpu_count() or 1
+    runs, t_start = [], time.perf_counter()
+    for num_envs, steps in ((1, 4), (min(cores, 4), 2)):
+        if time.perf_counter() - t_start > max_seconds:
+            break
+        value, elapsed = fe.env_steps_per_s(spec, feats, labels, num_envs, steps, warmup=0,
+                                            batch_size=BATCH, max_batches=400, max_history=HIST)
+        runs.append({'envs': num_envs, 'threads': num_envs, 'steps': steps, 'env_steps_per_s': value,
+                     'seconds': elapsed})
+    best = max(r['env_steps_per_s'] for r in runs)
+    return {'value': best, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port-faithful',
+            'runs': runs, 'rows': CPU_ROWS,
+            'sample': 'per-env Python env objects (History, per-agent dicts, 14 info statistics) over the '
+                      'oracle\'s numpy float32 problem, thread per env + pipes; extrapolation to 4096 envs is linear'}
+
+
 def cpu_env_steps_per_s(envs_per_thread, threads, steps, warmup):
     """The oracle's vectorised numpy path (float32 problem arithmetic, the reference's
     float64 env arithmetic), one oracle instance per host thread."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import optenv_oracle as orc
-    feats, labels = synthetic_data(4096)
+    feats, labels = synthetic_data(CPU_ROWS)
     spec = orc.ProblemSpec('softmax', D, (HID,), C)
     perm = orc.env_permutation(len(feats), 0)
 
@@ -176,8 +211,9 @@ def reference_arm(args):
     threads = min(cores, 32)
     envs_per_thread = 8
     value, elapsed = cpu_env_steps_per_s(envs_per_thread, threads, args.steps, args.warmup)
-    sample = '%d envs (%d threads x %d) x %d steps of the workload, oracle numpy float32' % (
-        envs_per_thread * threads, threads, envs_per_thread, args.steps)
+    sample = ('%d envs (%d threads x %d) x %d steps of the workload, oracle numpy float32, %d-row data set '
+              '(the GPU arm: 60000 rows; 32 rows per env-step are touched either way)' % (
+                  envs_per_thread * threads, threads, envs_per_thread, args.steps, CPU_ROWS))
     line = {
         'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -187,6 +223,7 @@ def reference_arm(args):
                    'note': 'reference algorithm (oracle port) on host CPU; TensorFlow/gym '
                            'are not installable so the reference itself cannot run'},
         'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+                         'threads': threads, 'envs_per_thread': envs_per_thread, 'rows': CPU_ROWS,
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -195,6 +232,46 @@ def reference_arm(args):
 
 
 # -------------------------------------------------------------------------- GPU arm
+def sampled_parity(env, feats, labels, actions, max_batches=MAX_BATCHES, depth=HIST, spec=None):
+    """One env step checked against the oracle for the sampled envs {0, 1, E/3, 2E/3, E-2, E-1}:
+    the oracle (the checker, oracle/step_check.py) is seeded with the device's own state of those
+    envs and replays the step; new weights, loss, reward, done and the newest observation
+    column of each block at the bar of the parity tests, the older columns bit for bit against
+    the previous observation.  Mutates ``env`` by that one step."""
+    import torch
+    from oracle import optenv_oracle as orc
+    from oracle import step_check
+    spec = spec or orc.ProblemSpec('softmax', D, (HID,), C)
+    num_envs, num_params = env.num_envs, env.num_params
+    sample = sorted({0, 1, num_envs // 3, 2 * num_envs // 3, num_envs - 2, num_envs - 1} & set(range(num_envs)))
+    pick = torch.as_tensor(sample, device=env.device)
+    perm = orc.lexicographic_rows(num_params)
+
+    def rows_of(tensor):                       # [E*P, ...] -> sampled envs, natural parameter order
+        rows = tensor.reshape(num_envs, num_params, -1)[pick].cpu().numpy()
+        nat = np.empty_like(rows)
+        nat[:, perm] = rows
+        return nat
+
+    idx, cnt = env.batch_indices()
+    state = {'params': env.get_state('params')[pick].cpu().numpy(),
+             'grad_prev': env.get_state('grad_prev')[pick].cpu().numpy(),
+             'loss_prev': env.get_state('raw_losses')[pick, 0].cpu().numpy(),      # newest entry of the raw loss history
+             'step': env.get_state('step')[pick].cpu().numpy(),
+             'idx': idx[pick].cpu().numpy(), 'cnt': cnt[pick].cpu().numpy()}
+    obs_prev = rows_of(env.obs)
+    act_nat = rows_of(actions)[:, :, 0]
+    obs, reward, done, info = env.step(actions)
+    device = {'params': env.get_state('params')[pick].cpu().numpy(), 'loss': info[pick, 1].cpu().numpy(),
+              'reward': reward[pick].cpu().numpy(), 'done': done[pick].cpu().numpy().astype(bool),
+              'obs': rows_of(obs), 'obs_prev': obs_prev}
+    ref, ref_obs, ref_reward, ref_done, _ = step_check.replay_step(spec, feats, labels, state, act_nat,
+                                                                   max_batches=max_batches, depth=depth)
+    stats = step_check.compare_step(ref, ref_obs, ref_reward, ref_done, state, device, depth=depth)
+    stats['envs'] = sample
+    return stats
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -219,13 +296,19 @@ def gpu_arm(args):
             numa_node = bind_to_gpu_numa(device_pci_bus_id(local))
         except (AttributeError, RuntimeError):
             numa_node = -1
-    envs = args.envs
     feats, labels = synthetic_data()
-    # envs shard by index: rank r owns envs [r*envs, (r+1)*envs); seeds follow the global index
-    seeds = range(rank * envs, (rank + 1) * envs)
+    # envs shard by index (custom_envs_b200/sharding.py): weak scaling gives every rank args.envs envs,
+    # --envs-total E shards E envs contiguously over the ranks (strong scaling); seeds follow the global index
+    if args.envs_total:
+        from custom_envs_b200.sharding import shard_range
+        first_env, envs = shard_range(args.envs_total, world, rank)
+        envs_all = args.envs_total
+    else:
+        first_env, envs, envs_all = rank * args.envs, args.envs, args.envs * world
+    seeds = range(first_env, first_env + envs)
     perms = env_permutations(ROWS, list(seeds))
     env = BatchedOptEnv(ProblemSpec('softmax', D, (HID,), C), feats, labels, envs,
-                        batch_size=BATCH, max_batches=400, max_history=HIST,
+                        batch_size=BATCH, max_batches=MAX_BATCHES, max_history=HIST,
                         row_order=args.row_order, perms=perms, device=device,
                         init_seed=1234 + rank)
     del perms
@@ -250,23 +333,44 @@ def gpu_arm(args):
         while not sampler.lines and time.time() < deadline:
             time.sleep(0.05)
         sampler.mark()
+    # one episode end inside the timed window: every env reaches max_batches at timed step K // 2
+    # and is re-initialised by the auto-reset that follows that step
+    reset_at = args.steps // 2
+    env.set_state('step', torch.full((envs,), MAX_BATCHES - reset_at - 1, dtype=torch.int32, device=device))
+    barrier()
     launches0 = env.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     done_total = 0
     start.record()
     for i in range(args.steps):
         env.step(actions[i & 1])
+        if i == reset_at:
+            done_total = env.done.sum()              # device tensor, read after the timed region
     stop.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = env.launch_count - launches0
     ms = start.elapsed_time(stop)
-    done_total = int(env.done.sum().item())
+    done_total = int(done_total.item()) if torch.is_tensor(done_total) else 0
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = envs * world * args.steps / (ms * 1e-3)
+    value = envs_all * args.steps / (ms * 1e-3)
+
+    # ---- parity: one more step, replayed by the oracle for six sampled envs from the device's own state
+    parity = sampled_parity(env, feats, labels, actions[0]) if rank == 0 else None
+
+    # ---- cost of a full re-initialisation of every env (b2e_reset), for the amortised figure
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    env.reset()
+    ev1.record()
+    torch.cuda.synchronize()
+    reset_ms = ev0.elapsed_time(ev1)
+    for i in range(3):                                  # back to a steady state with valid history rings
+        env.step(actions[i & 1])
 
     # ---- end to end through the reference-facing VecEnv call with host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -288,7 +392,7 @@ def gpu_arm(args):
         t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = envs * world * e2e_steps / e2e_s
+    e2e_value = envs_all * e2e_steps / e2e_s
     h2d = host_actions.nbytes
     d2h = states.nbytes + env.reward.numel() * 4 + env.done.numel() + env.info.numel() * 8
 
@@ -330,22 +434,28 @@ def gpu_arm(args):
         dominant = max(kernels, key=lambda k: k['ms']) if kernels else None
         launch_ms = ms / args.steps
         step_gbs = BYTES_PER_ENV_STEP * envs / (launch_ms * 1e-3) / 1e9
-        achieved = dominant['gbs'] if dominant else step_gbs
         cores = os.cpu_count() or 1
         threads = min(cores, 32)
         cpu_steps = 30                          # ~12 s of host work on the pool's 16-32 core boxes
         cpu_value, cpu_elapsed = cpu_env_steps_per_s(8, threads, cpu_steps, 1)
+        faithful = cpu_faithful() if not args.skip_faithful else None
         line = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'envs_per_gpu': envs, 'envs_total': envs * world,
-                       'agent_rows_total': envs * world * NUM_PARAMS, 'row_order': args.row_order,
+            'higher_is_better': True, 'scaling': 'strong' if args.envs_total else 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'envs_per_gpu': envs, 'envs_total': envs_all,
+                       'agent_rows_total': envs_all * NUM_PARAMS, 'row_order': args.row_order,
                        'actions': 'U[0,3) float32, resident in HBM',
                        'l2': 'per-step working set %.1f GB >> 126 MB L2 (no flush needed)'
                              % (BYTES_PER_ENV_STEP * envs / 1e9),
-                       'envs_done_last_step': done_total, 'parallelism': 'env-index shards, dp%d' % world},
+                       'episode_end_in_window': {'timed_step': reset_at, 'envs_done': done_total,
+                                                 'note': 'every env of rank 0 reaches max_batches there and is auto-reset'},
+                       'full_reset_ms': reset_ms,
+                       'reset_amortised_ms_per_step': {'at_400_steps': reset_ms / 400, 'at_100_steps': reset_ms / 100},
+                       'obs_tolerance': 'observations: 1e-5 relative on >= 98 % of the well-conditioned entries, '
+                                        '20e-5 on all of them (ratios of fp32 quantities, tests/test_gpu_parity.py)',
+                       'parallelism': 'env-index shards, dp%d' % world},
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps,
                     'api': 'DeviceOptVecEnv.step(numpy actions) -> numpy states/rewards/dones + infos',
@@ -354,17 +464,24 @@ def gpu_arm(args):
                     'ms_each_step': [round(1e3 * (b - a), 1) for a, b in zip(e2e_marks, e2e_marks[1:])]},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
-                         'kernel': dominant['name'] if dominant else 'optenv_kernel',
-                         'bytes_per_launch': dominant['bytes'] if dominant else BYTES_PER_ENV_STEP * envs,
-                         'kernels': kernels,
-                         'whole_step': {'achieved': step_gbs, 'frac': step_gbs / peak,
-                                        'bytes_per_step': BYTES_PER_ENV_STEP * envs,
-                                        'note': 'SURVEY 8d algorithmic bytes of the fused step / step time'}},
+            # headline = SURVEY 8d: algorithmic bytes of the WHOLE step / step time (episode end included);
+            # the dominant kernel and every pipeline kernel with its own bytes and duration beside it
+            'roofline': {'bound': 'hbm', 'achieved': step_gbs, 'peak': peak, 'unit': 'GB/s',
+                         'frac': step_gbs / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
+                         'what': 'whole step: 4*[P*(5H+3)+B*(D+1)] = %d bytes per env-step x %d envs / %.3f ms'
+                                 % (BYTES_PER_ENV_STEP, envs, launch_ms),
+                         'bytes_per_launch': BYTES_PER_ENV_STEP * envs,
+                         'dominant_kernel': ({'name': dominant['name'], 'achieved': dominant['gbs'],
+                                              'frac': dominant['gbs'] / peak, 'bytes_per_launch': dominant['bytes'],
+                                              'ms': dominant['ms']} if dominant else None),
+                         'kernels': [dict(k, frac=k['gbs'] / peak) for k in kernels]},
+            'parity': parity,
             'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                             'sample': '%d envs x %d steps of the workload (oracle numpy float32, '
-                                       '%d threads), %.1f s' % (8 * threads, cpu_steps, threads, cpu_elapsed)},
+                             'threads': threads, 'envs_per_thread': 8, 'rows': CPU_ROWS,
+                             'sample': '%d envs x %d steps of the workload (oracle vectorised numpy float32, '
+                                       '%d threads x 8 envs, %d-row data set), %.1f s'
+                                       % (8 * threads, cpu_steps, threads, CPU_ROWS, cpu_elapsed),
+                             'faithful': faithful},
         }
         print(json.dumps(line), flush=True)
     env.close()
@@ -381,6 +498,9 @@ def main():
     parser.add_argument('--envs', type=int, default=4096, help='envs per GPU')
     parser.add_argument('--row-order', default='lexicographic', choices=['lexicographic', 'natural'])
     parser.add_argument('--e2e-steps', type=int, default=5)
+    parser.add_argument('--envs-total', type=int, default=0,
+                        help='strong scaling: this many envs sharded over all ranks (overrides --envs)')
+    parser.add_argument('--skip-faithful', action='store_true', help='skip the ~25 s per-env-object CPU baseline')
     args = parser.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

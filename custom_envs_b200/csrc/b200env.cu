@@ -3691,10 +3691,12 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (occ_tc > 512 / tc::TMEM_COLS) occ_tc = 512 / tc::TMEM_COLS;    // TMEM: 512 columns per SM
         h->tc_grid = occ_tc * h->num_sms;
     }
-    {   // tcgen05 eval kernel, warp-specialised (B2E_TC=2); its context is made once the state
+    {   // tcgen05 eval kernel, warp-specialised (b200tc.cu); its context is made once the state
         // buffers exist (the tensor map holds the address of w)
+        // default for the shapes it covers (B2E_TC=0: the FFMA eval kernels, B2E_TC=1: the first,
+        // single-role tcgen05 kernel kept for comparison)
         const char *tcv = getenv("B2E_TC");
-        h->use_tc2 = h->use_eval_kernel && tcv && atoi(tcv) == 2 && b2e_tc2_supported(&h->d);
+        h->use_tc2 = h->use_eval_kernel && (!tcv || atoi(tcv) == 2) && b2e_tc2_supported(&h->d);
         if (h->use_tc2) {
             h->tc2_check = getenv("B2E_TC_CHECK") && atoi(getenv("B2E_TC_CHECK")) != 0;
             h->use_tc = false;

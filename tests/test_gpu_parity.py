@@ -606,6 +606,7 @@ def test_fused_update_variant_equals_the_four_kernel_pipeline(monkeypatch):
     labels = rng.randint(0, 10, 256).astype(np.int32)
     runs = []
     for fused in (False, True):
+        monkeypatch.setenv('B2E_TC', '0')                   # the fusion lives in the FFMA eval kernel
         if fused:
             monkeypatch.setenv('B2E_FUSE_UPDATE', '1')
         else:
@@ -626,3 +627,53 @@ def test_fused_update_variant_equals_the_four_kernel_pipeline(monkeypatch):
     for (obs_a, rew_a, done_a, info_a), (obs_b, rew_b, done_b, info_b) in zip(runs[0][0], runs[1][0]):
         assert np.array_equal(obs_a, obs_b) and np.array_equal(rew_a, rew_b) and np.array_equal(done_a, done_b)
         assert np.allclose(info_a, info_b, rtol=1e-6, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize('after_reset', [False, True])
+def test_bench_sampled_parity_check_agrees_with_the_step(after_reset):
+    """bench.py's ``parity`` entry (oracle/step_check.py seeded with the device's own state) on a
+    small MLP batch: green on a correct step, also right after an auto-reset, and red when the
+    device's weights are tampered with."""
+    import bench
+    BatchedOptEnv, _ = _mods()
+    spec = orc.ProblemSpec('softmax', 784, (64,), 10)
+    feats, labels = make_data(spec, 512)
+    env = BatchedOptEnv(product_spec(spec), feats, labels, 9, batch_size=32, max_batches=4, init_seed=2)
+    env.reset()
+    gen = torch.Generator(device=env.device)
+    gen.manual_seed(1)
+    actions = torch.rand(env.num_rows, device=env.device, generator=gen) * 3.0
+    for _ in range(4 if after_reset else 1):
+        env.step(actions)
+    stats = bench.sampled_parity(env, feats, labels, actions, max_batches=4, spec=spec)
+    assert stats['ok'], stats
+    assert stats['history_shift_exact'] and stats['done_equal'] and stats['max_rel_err'] <= 2e-4
+    assert stats['envs'] == [0, 1, 3, 6, 7, 8]
+    # a wrong step must be seen: scale the device's weights behind the checker's back
+    if after_reset:
+        env.step(actions)
+    state = env.get_state('params')
+    obs_before = env.obs.clone()
+    import oracle.step_check as step_check
+    idx, cnt = env.batch_indices()
+    pick = torch.as_tensor(stats['envs'], device=env.device)
+    seeded = {'params': (state[pick] * 1.001).cpu().numpy(), 'grad_prev': env.get_state('grad_prev')[pick].cpu().numpy(),
+              'loss_prev': env.get_state('raw_losses')[pick, 0].cpu().numpy(), 'step': env.get_state('step')[pick].cpu().numpy(),
+              'idx': idx[pick].cpu().numpy(), 'cnt': cnt[pick].cpu().numpy()}
+    perm = orc.lexicographic_rows(env.num_params)
+    act_nat = np.empty((len(stats['envs']), env.num_params), np.float32)
+    act_nat[:, perm] = actions.reshape(env.num_envs, env.num_params)[pick].cpu().numpy()
+    ref, ref_obs, ref_rew, ref_done, _ = step_check.replay_step(spec, feats, labels, seeded, act_nat, max_batches=4)
+    obs, reward, done, info = env.step(actions)
+
+    def rows(t):
+        r = t.reshape(env.num_envs, env.num_params, -1)[pick].cpu().numpy()
+        nat = np.empty_like(r)
+        nat[:, perm] = r
+        return nat
+    device = {'params': env.get_state('params')[pick].cpu().numpy(), 'loss': info[pick, 1].cpu().numpy(),
+              'reward': reward[pick].cpu().numpy(), 'done': done[pick].cpu().numpy().astype(bool),
+              'obs': rows(obs), 'obs_prev': rows(obs_before)}
+    bad = step_check.compare_step(ref, ref_obs, ref_rew, ref_done, seeded, device)
+    assert not bad['ok']
+    env.close()
