@@ -88,6 +88,7 @@ class BatchedOptEnv:
         cfg.struct_size = ctypes.sizeof(_lib.Config)
         cfg.device = self.device.index or 0
         cfg.env_kind = _lib.ENV_MULTIOPTLRS if env_kind == 'optlrs' else _lib.ENV_MULTIOPTIMIZE
+        self.env_kind_name = 'optlrs' if env_kind == 'optlrs' else 'optimize'
         cfg.problem_kind = _PROBLEM_KINDS[problem.kind]
         func = problem.kind == 'func'
         if not func:
@@ -215,6 +216,38 @@ class BatchedOptEnv:
                                       _ptr(self.reward), _ptr(self.done), _ptr(self.info),
                                       self._stream()))
         return obs, self.reward, self.done, self.info
+
+    def capture_step_graph(self, actions, steps=None):
+        """Record the batched step into a CUDA graph (``b2e_step`` enqueues kernels on the caller's
+        stream and nothing else: no allocation, no synchronisation, no host read-back).
+
+        ``actions`` is the static device buffer the replays read; refill it in place between
+        replays.  The kernel pipeline of the large problems alternates between two gradient
+        buffers, so one replay covers TWO consecutive steps there (``steps`` defaults to that
+        period; the small fused problems replay one step).  Returns ``(graph, steps)``;
+        ``graph.replay()`` leaves the outputs of the last step in ``self.obs / reward / done / info``.
+        Host-supplied minibatch indices (index_mode='external') cannot be captured."""
+        if self.index_mode != 'internal' and self.problem.kind != 'func':
+            raise _lib.B200EnvError('capture_step_graph needs the on-device minibatch stream')
+        actions = actions.reshape(-1)
+        assert actions.dtype == torch.float32 and actions.device == self.device and actions.is_contiguous()
+        period = 2 if self.num_params >= 4096 or self.env_kind_name == 'optimize' else 1
+        steps = period if steps is None else int(steps)
+        if steps % period:
+            raise _lib.B200EnvError('this problem replays in multiples of %d steps' % period)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.step(actions)                       # warm-up outside the capture (lazy module loading)
+            if period == 2:
+                self.step(actions)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            for _ in range(steps):
+                self.step(actions)
+        return graph, steps
 
     def evaluate(self, batch_idx=None, batch_cnt=None):
         """BaseProblem.get for every env: (grad [E,P], loss [E]) on the current minibatch."""

@@ -17,13 +17,15 @@
 //   warp 2      XB producer : minibatch rows [32 s][128 f] of a backward tile (L2 hits), 16-byte cp.async
 //   warps 3, 23 MMA issuers : forward units / backward tiles, one elected lane each, two independent
 //                             in-order queues; the tail of env k runs under the forward stream of env k+1
-//   warps 4-7   tail        : TMEM -> Hpre, bias/relu/layer 2/softmax-CE/backward -> dPre operand
+//   warps 4-7   tail        : Hpre -> bias/relu/layer 2/softmax-CE/backward -> dPre operand, tail gradient
 //   warps 8-11  drain       : gradient tiles TMEM -> registers -> shared-memory transpose -> HBM;
 //                             second eval: the step's scalars (reward, done, info, cursor)
-//   warps 12-22 converters  : lo parts of every landed operand tile (12-19 forward ring, 20-22 backward ring)
+//   warps 12-15, 20-22 converters : lo parts of every landed operand tile (forward ring / backward ring)
+//   warps 16-19 read-out    : forward accumulators TMEM -> fp32 registers every two units (short sums inside
+//                             the truncating tensor-core adder), Hpre of the env -> tail group
 // Pipelines: forward ring (4 stages x 24 KB: W hi/lo, X hi/lo), backward ring (2 x 32 KB: X hi/lo),
-// both full -> converted -> (tcgen05.commit) empty; TMEM: four forward accumulators [128 x 64] (every
-// fourth unit each: the tensor core's adder truncates, so long sums are split and added by threads) and
+// both full -> converted -> (tcgen05.commit) empty; TMEM: four forward accumulators [128 x 64] (two
+// units each, then read out: the tensor core's adder truncates, so long sums are added by threads) and
 // two gradient accumulators [128 x 128], with full / free mbarrier pairs.
 //
 // Shared-memory operand layouts (UMMA canonical, 128-byte rows):
@@ -63,9 +65,9 @@ constexpr int T_H = 0, T_TW = T_H + N1 * HS, T_TG = T_TW + TW_MAX, T_ZP = T_TG +
               T_YS = T_Z + B * CMAX, T_GP = T_YS + B, T_MISC = T_GP + 2 * N1, T_END = T_MISC + 16;
 constexpr int SMEM_BYTES = OFF_TAIL + T_END * 4 + 1024;   // + slack to align the base to 1024 bytes
 constexpr int TMEM_COLS = 512;                        // forward 4 x 64, gradient 2 x 128 columns
-constexpr int TM_F = 0, TM_G = 256, NACC = 4;
+constexpr int TM_F = 0, TM_G = 256, NACC = 4, GRP = 1;     // forward accumulators; units summed inside the tensor core per read-out
 constexpr int THREADS = 768;                          // 24 warps, at most 80 registers each
-constexpr int CONV_F_WARPS = 8, CONV_B_WARPS = 3, MMA_B_WARP = 23;
+constexpr int CONV_F_WARPS = 4, READ_WARP0 = 16, CONV_B_WARP0 = 20, CONV_B_WARPS = 3, MMA_B_WARP = 23;
 constexpr int DBG_BYTES = 64 + 8 * 512 * 8;
 constexpr long long WATCHDOG_CYCLES = 1500000000LL;   // ~0.8 s: a wait this long is a protocol bug
 
@@ -73,7 +75,7 @@ struct Bars {
     uint64_t fullF[SF], convF[SF], emptyF[SF];
     uint64_t fullB[SB], convB[SB], emptyB[SB];
     uint64_t g_full[2], g_free[2], tail_done[2];
-    uint64_t fwd_done, fwd_free, dpre_ready, dpre_free;
+    uint64_t acc_full[NACC], acc_free[NACC], hpre_ready, hpre_free, dpre_ready, dpre_free;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,8 +192,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bars.g_full[s], 1); mbar_init(&bars.g_free[s], 4); mbar_init(&bars.tail_done[s], 1);
         }
-        mbar_init(&bars.fwd_done, 1); mbar_init(&bars.fwd_free, 4);
+        for (int s = 0; s < NACC; ++s) { mbar_init(&bars.acc_full[s], 1); mbar_init(&bars.acc_free[s], 4); }
         mbar_init(&bars.dpre_ready, 1); mbar_init(&bars.dpre_free, 1);
+        mbar_init(&bars.hpre_ready, 2); mbar_init(&bars.hpre_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -308,27 +311,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             const uint32_t idesc_f = TF32 | (1u << 15) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // A MN-major, B K-major
             const uint64_t ad0 = make_desc(sbase + OFF_F + F_W, 4096, 512, 1);
             const uint64_t bd0 = make_desc(sbase + OFF_F + F_X, 16, 1024, 2);
-            uint32_t itF = 0;
-            int k = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
-                mbar_wait(&bars.fwd_free, (k & 1) ^ 1, 7, dbg);   // the tail has read the accumulators of env k-1
+            uint32_t itF = 0, itP = 0;
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
                 for (int u = 0; u < UF; ++u, ++itF) {
-                    const int s = itF % SF;
+                    const int s = itF % SF, b = itP % NACC;
+                    // The tensor core's adder truncates: a sum over all 98 K steps in ONE accumulator drifts by
+                    // ~1e-6 of the result (and 25 steps still by ~3x the error of an fp32 FFMA chain, which the
+                    // full-size parity test catches in the gradient ratios).  GRP units (8 MMAs) are summed per
+                    // accumulator; the tail group reads it out and keeps the running sum in fp32 registers.
+                    if (u % GRP == 0) mbar_wait(&bars.acc_free[b], ((itP / NACC) & 1) ^ 1, 7, dbg);
                     mbar_wait(&bars.convF[s], (itF / SF) & 1, 8, dbg);
                     tc_fence_after();
+                    const bool last = u % GRP == GRP - 1 || u == UF - 1;
                     if (elect_one()) {
                         const uint64_t ad = ad0 + (uint64_t)(s * (F_STAGE >> 4)), bd = bd0 + (uint64_t)(s * (F_STAGE >> 4));
-                        // The tensor core's adder truncates: a sum over all 98 K steps in ONE accumulator
-                        // drifts by ~1e-6 of the result.  Four accumulators take every fourth unit
-                        // (<= 28 steps each) and the tail adds them in fp32 round-to-nearest.
-                        const uint32_t acc = tmem + TM_F + 64 * (u & (NACC - 1));
+                        const uint32_t acc = tmem + TM_F + 64 * b;
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)   // 8 features per MMA: 1024 bytes of A, 32 bytes of B
-                            mma_tf32(acc, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 2), idesc_f, (u >= NACC || kk) ? 1u : 0u);
+                            mma_tf32(acc, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 2), idesc_f, (u % GRP || kk) ? 1u : 0u);
                         mma_commit(&bars.emptyF[s]);
-                        if (u == UF - 1) mma_commit(&bars.fwd_done);
+                        if (last) mma_commit(&bars.acc_full[b]);
                     }
                     __syncwarp();
+                    if (last) ++itP;
                     TC2_TRACE(3, itF);
                 }
             }
@@ -391,39 +396,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                 else tw[N1 + N1 * CMAX + (r - N1 * C)] = v;
             }
             if (ttid < B) ys[ttid] = ttid < cnt ? d.labels[idx[ttid]] : 0;
-            // ---- forward accumulators: lanes 0..63 = W_hi rows, 64..127 = W_lo rows; columns 0..31 = X_hi, 32..63 = X_lo
-            mbar_wait(&bars.fwd_done, k & 1, 9, dbg);
+            // ---- Hpre = X . W1 arrives from the read-out group in HT; + bias, relu (rows the minibatch does not have stay 0)
+            mbar_wait(&bars.hpre_ready, k & 1, 9, dbg);
             if (q == 0) TC2_TRACE(5, 2 * k);
-            tc_fence_after();
-            float acc[32];
             {
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_F;
-                const int nacc = UF < NACC ? UF : NACC;
+                const int jj = ttid & 63, sg = ttid >> 6;
+                const float bj = b1[jj];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-                for (int c = 0; c < 2 * nacc; ++c) {      // the X_lo halves of the accumulators first (small terms), then the X_hi halves
-                    uint32_t v[32];
-                    TC2_LD32(taddr + 64 * (c % nacc) + (c < nacc ? 32 : 0), v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.fwd_free);
-            const int j = (q & 1) * 32 + lane;
-            if (q >= 2) {
-#pragma unroll
-                for (int s = 0; s < B; ++s) HT[j * HS + s] = acc[s];
-            }
-            group_bar(1);
-            if (q < 2) {                                  // + bias, relu (rows the minibatch does not have stay 0)
-                const float bj = b1[j];
-#pragma unroll
-                for (int s = 0; s < B; ++s) {
-                    const float v = (HT[j * HS + s] + acc[s]) + bj;
-                    HT[j * HS + s] = (s < cnt && v > 0.f) ? v : 0.f;
+                for (int i = 0; i < 16; ++i) {
+                    const int s = sg * 16 + i;
+                    const float v = HT[jj * HS + s] + bj;
+                    HT[jj * HS + s] = (s < cnt && v > 0.f) ? v : 0.f;
                 }
             }
             group_bar(1);
@@ -571,6 +554,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                 a.loss_out[e] = tmisc[0];
             }
             group_bar(1);                                 // scratch is reused by the next env
+            if (ttid == 0) mbar_arrive(&bars.hpre_free);  // the read-out group may write the next env's Hpre
         }
     } else if (warp >= 8 && warp < 12) {
         // ===================== drain group (128 threads, named barrier 2): gradient tiles -> HBM
@@ -652,7 +636,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         // threads with a few float4 each: what counts is the latency of a unit, not the throughput
         // (every microsecond a stage spends here is a microsecond it is not in flight to HBM).
         if (warp >= 12 && warp < 12 + CONV_F_WARPS) {
-            const int cid = tid - 384;                    // 0..255
+            const int cid = tid - 384;                    // 0..127
             uint32_t itF = 0;
             for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
                 for (int u = 0; u < UF; ++u, ++itF) {
@@ -662,16 +646,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                     unsigned char *base = sm + OFF_F + s * F_STAGE;
                     // loads first, stores after: the compiler cannot move a shared-memory load above an
                     // earlier store to the same array
-                    float4 v[3];
+                    float4 v[6];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {         // 512 float4 of W, then 256 of X
-                        const int c = i * 256 + cid;
-                        v[i] = *reinterpret_cast<const float4 *>(base + (i < 2 ? F_W + c * 16 : F_X + (c - 512) * 16));
+                    for (int i = 0; i < 6; ++i) {         // 512 float4 of W, then 256 of X
+                        const int c = i * 128 + cid;
+                        v[i] = *reinterpret_cast<const float4 *>(base + (i < 4 ? F_W + c * 16 : F_X + (c - 512) * 16));
                     }
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int c = i * 256 + cid;
-                        *reinterpret_cast<float4 *>(base + (i < 2 ? F_WLO + c * 16 : F_XLO + (c - 512) * 16)) = lo_of4(v[i]);
+                    for (int i = 0; i < 6; ++i) {
+                        const int c = i * 128 + cid;
+                        *reinterpret_cast<float4 *>(base + (i < 4 ? F_WLO + c * 16 : F_XLO + (c - 512) * 16)) = lo_of4(v[i]);
                     }
                     fence_async();
                     __syncwarp();
@@ -679,8 +663,52 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                     if (warp == 12) TC2_TRACE(2, itF);
                 }
             }
-        } else if (warp >= 12 + CONV_F_WARPS && warp < 12 + CONV_F_WARPS + CONV_B_WARPS) {
-            const int cid = tid - 384 - 32 * CONV_F_WARPS;   // 0..95
+        } else if (warp >= READ_WARP0 && warp < READ_WARP0 + 4) {
+            // ===================== read-out group (128 threads, named barrier 3): the forward accumulators.
+            // Lanes 0..63 of an accumulator = W_hi rows, 64..127 = W_lo rows; columns 0..31 = X_hi, 32..63 = X_lo.
+            // One read-out per GRP units; the running sum of the env lives in registers (fp32, round to
+            // nearest); at the end of the env the four partial products meet in HT [64 j][32 s].
+            const int q = warp - READ_WARP0;
+            float *HT = ts + T_H;
+            uint32_t itP = 0;
+            int k = 0;
+            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+                for (int u0 = 0; u0 < UF; u0 += GRP, ++itP) {
+                    const int b = itP % NACC;
+                    mbar_wait(&bars.acc_full[b], (itP / NACC) & 1, 15, dbg);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_F + 64 * b;
+#pragma unroll
+                    for (int half = 1; half >= 0; --half) {   // the X_lo columns (small terms) first
+                        uint32_t v[32];
+                        TC2_LD32(taddr + 32 * half, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v[i]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.acc_free[b]);
+                }
+                if (k >= 1) mbar_wait(&bars.hpre_free, (k - 1) & 1, 16, dbg);     // the tail is done with the previous env's activations
+                const int j = (q & 1) * 32 + lane;
+                if (q >= 2) {
+#pragma unroll
+                    for (int s = 0; s < B; ++s) HT[j * HS + s] = acc[s];
+                }
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                if (q < 2) {
+#pragma unroll
+                    for (int s = 0; s < B; ++s) HT[j * HS + s] += acc[s];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.hpre_ready);
+                }
+            }
+        } else if (warp >= CONV_B_WARP0 && warp < CONV_B_WARP0 + CONV_B_WARPS) {
+            const int cid = tid - 32 * CONV_B_WARP0;        // 0..95
             uint32_t itB = 0;
             for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
                 for (int t = 0; t < TB; ++t, ++itB) {

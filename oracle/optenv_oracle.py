@@ -115,7 +115,7 @@ def _unflatten(spec, theta):
     return arrays
 
 
-def loss_and_grad(spec: ProblemSpec, theta, feats, targs, mask, dtype=np.float64):
+def loss_and_grad(spec: ProblemSpec, theta, feats, targs, mask, dtype=np.float64, abs_terms=False):
     """Batched forward/backward.
 
     theta [E,P]; feats [E,B,D]; targs [E,B] int labels ('softmax') or [E,B,C] floats
@@ -124,6 +124,9 @@ def loss_and_grad(spec: ProblemSpec, theta, feats, targs, mask, dtype=np.float64
     Returns (grad [E,P] = d(SUM_i loss_i)/d theta, loss [E] = MEAN_i loss_i), which is
     what ``tf.gradients(loss_vec, w)`` and ``tf.reduce_mean(loss_vec)`` produce
     (problems/optimize_nn.py:47-52).
+    ``abs_terms=True`` appends S [E,P], the sum of the ABSOLUTE terms of the last dot product behind
+    every gradient element (|activations|^T . |deltas|): the scale fp32 rounding noise of that
+    element is proportional to, which the parity tests bound the device's error with.
     """
     theta = np.asarray(theta, dtype)
     num_envs = theta.shape[0]
@@ -166,13 +169,19 @@ def loss_and_grad(spec: ProblemSpec, theta, feats, targs, mask, dtype=np.float64
     loss = (per_sample * mask).sum(axis=1) / count
     dout = dout * mask[..., None]
     grads = [None] * len(params)
+    sums = [None] * len(params)
     for li in reversed(range(nlayers)):
         grads[2 * li] = np.matmul(acts[li].transpose(0, 2, 1), dout)
         grads[2 * li + 1] = dout.sum(axis=1)
+        if abs_terms:
+            sums[2 * li] = np.matmul(np.abs(acts[li]).transpose(0, 2, 1), np.abs(dout))
+            sums[2 * li + 1] = np.abs(dout).sum(axis=1)
         if li > 0:
             dout = np.matmul(dout, params[2 * li].transpose(0, 2, 1))
             dout = dout * (pres[li - 1] > 0)
     grad = np.concatenate([g.reshape(num_envs, -1) for g in grads], axis=1)
+    if abs_terms:
+        return grad, loss, np.concatenate([t.reshape(num_envs, -1) for t in sums], axis=1)
     return grad, loss
 
 

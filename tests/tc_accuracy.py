@@ -20,7 +20,7 @@ idx = rng.randint(0, num_rows, size=(num_envs, batch)).astype(np.int32)
 cnt = np.full(num_envs, batch, np.int32)
 cnt[-1] = 11
 mask = np.arange(batch)[None, :] < cnt[:, None]
-ref_g, ref_l = orc.loss_and_grad(spec, params, feats[idx], labels[idx], mask)
+ref_g, ref_l, terms = orc.loss_and_grad(spec, params, feats[idx], labels[idx], mask, abs_terms=True)
 scale = np.abs(ref_g).mean(axis=1, keepdims=True)
 for mode in ('0', '2'):
     os.environ['B2E_TC'] = mode
@@ -33,7 +33,10 @@ for mode in ('0', '2'):
     grad, loss = grad.cpu().numpy().astype(np.float64), loss.cpu().numpy().astype(np.float64)
     err = np.abs(grad - ref_g) / np.maximum(np.abs(ref_g), scale)
     w1 = slice(0, 784 * 64)
+    noise = np.abs(grad - ref_g) / np.maximum(terms, 1e-30)
     print('B2E_TC=%s  loss rel err max %.2e | grad err / max(|g|, mean|g|): max %.2e  p99.9 %.2e  mean %.2e | W1 part max %.2e, tail part max %.2e'
           % (mode, np.max(np.abs(loss - ref_l) / np.abs(ref_l)), err.max(), np.quantile(err, 0.999), err.mean(),
              err[:, w1].max(), err[:, 784 * 64:].max()), flush=True)
+    print('          |error| / sum|terms| of the element: max %.2e  p99.99 %.2e  p99.9 %.2e  mean %.2e' % (
+        noise.max(), np.quantile(noise, 0.9999), np.quantile(noise, 0.999), noise.mean()), flush=True)
     env.close()

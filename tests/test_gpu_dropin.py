@@ -379,3 +379,44 @@ def test_integration_training_loop_snippet(tmp_path):
     env.close()
     assert finished == len(rows) >= 2 * 64 and all(row['l'] <= 6 for row in rows)
     assert (tmp_path / 'monitor.mon.csv').is_file()
+
+
+@pytest.mark.parametrize('shape', ['iris', 'mlp'])
+def test_step_replayed_from_a_cuda_graph_equals_eager_steps(shape):
+    """include/b200env.h promises that b2e_step only enqueues work on the caller's stream (no hidden
+    synchronisation or allocation): the step is captured into a CUDA graph and the replays must
+    reproduce the eager trajectory bit for bit, episode ends and auto-resets included."""
+    import torch
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec
+    rng = np.random.RandomState(0)
+    if shape == 'iris':
+        spec, rows, envs = ProblemSpec('softmax', 4, (), 3), 150, 64
+    else:
+        spec, rows, envs = ProblemSpec('softmax', 784, (64,), 10), 512, 6
+    feats = rng.uniform(size=(rows, spec.num_features)).astype(np.float32)
+    labels = rng.randint(0, spec.num_outputs, rows).astype(np.int32)
+
+    def make():
+        env = BatchedOptEnv(spec, feats, labels, envs, batch_size=32, max_batches=5, init_seed=4)
+        env.reset()
+        return env
+
+    eager, graphed = make(), make()
+    actions = torch.rand(eager.num_rows, device=eager.device, generator=torch.Generator(device=eager.device).manual_seed(9)) * 3
+    static = actions.clone()
+    graph, period = graphed.capture_step_graph(static)
+    assert period == (1 if shape == 'iris' else 2)
+    warm = period                                   # capture_step_graph ran `period` warm-up steps
+    for _ in range(warm):
+        eager.step(actions)
+    for replay in range(6):
+        graph.replay()
+        for _ in range(period):
+            obs, reward, done, info = eager.step(actions)
+        torch.cuda.synchronize()
+        assert torch.equal(graphed.obs, obs) and torch.equal(graphed.reward, reward), (shape, replay)
+        assert torch.equal(graphed.done, done)
+        assert torch.allclose(graphed.info, info, rtol=0, atol=0, equal_nan=True)
+    assert torch.equal(graphed.get_state('params'), eager.get_state('params'))
+    eager.close()
+    graphed.close()
