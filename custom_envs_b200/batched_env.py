@@ -146,7 +146,11 @@ class BatchedOptEnv:
                 assert perms.shape[-1] == num_rows and (not per_env or perms.shape[0] == self.num_envs)
                 perms = torch.as_tensor(perms).to(dev)
                 if init_orders is not None:
-                    init_orders = torch.as_tensor(np.ascontiguousarray(init_orders, np.int32)).to(dev)
+                    if torch.is_tensor(init_orders):        # e.g. built on the device for very many envs
+                        init_orders = init_orders.to(dev, torch.int32).contiguous()
+                    else:
+                        init_orders = torch.as_tensor(np.ascontiguousarray(init_orders, np.int32)).to(dev)
+                    assert tuple(init_orders.shape) == (self.num_envs, num_rows)
                 self._check(self.lib.b2e_set_index_stream(handle, _ptr(perms), per_env,
                                                           _ptr(init_orders), self._stream()))
             torch.cuda.synchronize(dev)       # library copied what it needs
