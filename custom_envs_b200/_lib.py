@@ -26,7 +26,9 @@ EXPORTS = (
     'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count',
     # data front-end (include/b200data.h)
     'b2d_last_error', 'b2d_resize_nearest', 'b2d_minmax_workspace', 'b2d_column_minmax',
-    'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot')
+    'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot',
+    # shared per-agent policy (include/b200policy.h)
+    'b2p_create', 'b2p_destroy', 'b2p_last_error', 'b2p_set_weights', 'b2p_act', 'b2p_act_env')
 DTYPE_U8, DTYPE_I32, DTYPE_F32, DTYPE_F64 = range(4)
 
 
@@ -91,6 +93,15 @@ def load():
     lib.b2d_rank_workspace.restype = usize
     lib.b2d_label_ranks.argtypes = [vp, i64, vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
     lib.b2d_onehot.argtypes = [vp, i64, i32, vp, i32, vp, vp]
+    f32, u64 = ctypes.c_float, ctypes.c_uint64
+    lib.b2p_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
+    lib.b2p_destroy.argtypes = [vp]
+    lib.b2p_destroy.restype = None
+    lib.b2p_last_error.argtypes = [vp]
+    lib.b2p_last_error.restype = ctypes.c_char_p
+    lib.b2p_set_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b2p_act.argtypes = [vp, vp, i64, vp, f32, u64, f32, f32, vp]
+    lib.b2p_act_env.argtypes = [vp, vp, vp, f32, u64, f32, f32, vp]
     if lib.b2e_abi_version() != 2:
         raise B200EnvError('libb200env.so ABI version mismatch')
     _lib = lib

@@ -74,7 +74,11 @@ class BatchedOptEnv:
                  batch_size=32, max_batches=400, max_history=5, env_kind='optlrs',
                  history_version=3, observation_version=3, action_version=0, reward_version=6,
                  row_order='lexicographic', index_mode='internal', auto_reset=True,
-                 seeds=None, perms=None, init_orders=None, device='cuda:0', init_seed=0):
+                 seeds=None, perms=None, init_orders=None, device='cuda:0', init_seed=0,
+                 materialize_obs=True):
+        """``materialize_obs=False``: no [E*P, obs_dim] observation matrix is allocated (12.5 GB at
+        BASELINE config 4); every step is then ring-only and the consumer reads the adjusted-history
+        rings in place (``custom_envs_b200.vectorize.device_policy.DevicePolicy.act_env``)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.B200EnvError('BatchedOptEnv needs a CUDA device (no CPU fallback)')
@@ -122,7 +126,8 @@ class BatchedOptEnv:
         self.history_depth = self.lib.b2e_history_depth(handle)
         self.num_rows = self.num_envs * self.num_params
         dev = self.device
-        self.obs = torch.empty((self.num_rows, self.obs_dim), dtype=torch.float32, device=dev)
+        self.obs = (torch.empty((self.num_rows, self.obs_dim), dtype=torch.float32, device=dev)
+                    if materialize_obs else None)
         self.reward = torch.zeros(self.num_envs, dtype=torch.float32, device=dev)
         self.done = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
         self.info = torch.zeros((self.num_envs, _lib.INFO_STRIDE), dtype=torch.float64, device=dev)
@@ -203,19 +208,24 @@ class BatchedOptEnv:
                                        _ptr(self.obs), self._stream()))
         return self.obs
 
-    def step(self, actions, batch_idx=None, batch_cnt=None, obs_out=None):
+    def step(self, actions, batch_idx=None, batch_cnt=None, obs_out=None, ring_only=False):
         """actions: [E*P] (or [E*P,1]) float32 device tensor in VecEnv row order.
         -> (obs [E*P,obs_dim], reward [E] f32, done [E] u8, info [E,16] f64): views of
         buffers that the next step overwrites.  ``obs_out``: write the observation rows there
         instead (any device-accessible float32 buffer of that shape, e.g. pinned host memory:
-        the rows then cross PCIe straight from the observation kernel)."""
+        the rows then cross PCIe straight from the observation kernel).  ``ring_only``: do not
+        write observation rows at all (obs is None in the result): the adjusted-history rings are
+        the observation, read in place by a device policy (MultiOptLRs, large problems)."""
         actions = actions.reshape(-1)
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, torch.float32).contiguous()
         assert actions.numel() == self.num_rows
         idx, cnt = self._idx(batch_idx, batch_cnt)
         obs = self.obs if obs_out is None else obs_out
-        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.obs.numel()
+        if ring_only or obs is None:
+            obs = None
+        else:
+            assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.numel() == self.num_rows * self.obs_dim
         self._check(self.lib.b2e_step(self.handle, _ptr(actions), _ptr(idx), _ptr(cnt), _ptr(obs),
                                       _ptr(self.reward), _ptr(self.done), _ptr(self.info),
                                       self._stream()))

@@ -28,6 +28,7 @@
 
 #include "b200env_shared.cuh"
 #include "b200tc.h"
+#include "b200env_internal.h"
 
 namespace {
 
@@ -2558,7 +2559,7 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Dev
 #pragma unroll
         for (int j = 0; j < 4; ++j) av[i][j] = (pq[i] + j < d.P) ? act[rows[j]] : 0.f;
     }
-    float s_absw = 0.f;
+    float s_absw = 0.f, s_absaw = 0.f;
     double s_lr = 0.0, s_lr2 = 0.0;
 #pragma unroll
     for (int i = 0; i < UPD_QUADS; ++i) {
@@ -2573,6 +2574,7 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Dev
             aw[j] = ratio_nn(wn[j], wv[j]);                      // utils_env.py:158-159
             if (pq[i] + j < d.P) {
                 s_absw += fabsf(wn[j]);
+                s_absaw += fabsf(aw[j]);
                 s_lr += (double)lr;
                 s_lr2 += (double)lr * (double)lr;
             } else {
@@ -2585,11 +2587,12 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Dev
     __shared__ double red[8 * 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double v0 = warp_sum((double)s_absw), v1 = warp_sum(s_lr), v2 = warp_sum(s_lr2);
-    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; }
+    const double v3 = warp_sum((double)s_absaw);             // sum |adjusted weights| of the new ring slot
+    if (lane == 0) { red[warp * 4] = v0; red[warp * 4 + 1] = v1; red[warp * 4 + 2] = v2; red[warp * 4 + 3] = v3; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double *out = d.part_u + ((size_t)e * d.nsegU + seg) * 4;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             double v = 0.0;
             for (int w = 0; w < 8; ++w) v += red[w * 4 + i];
             out[i] = v;
@@ -2597,15 +2600,107 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Dev
     }
 }
 
+// Ring-only step (b2e_step with obs_out = NULL): what obs_kernel does minus the observation
+// rows -- the adjusted gradient g_t / |g_{t-1}| (utils_env.py:156-157) into the newest ring slot and the
+// partial sums of adjusted_grad / grad_diff.  Parameter space, float4, fully coalesced: 2 words read and
+// 1 written per parameter instead of 26.  A consumer reads the rings in place (b2p_act_env).
+__global__ void __launch_bounds__(256) ring_adjg_kernel(const __grid_constant__ Dev d,
+                                                        const __grid_constant__ StepArgs a) {
+    const int e = a.e_begin + blockIdx.y;
+    const int seg = blockIdx.x;
+    const EnvScalars *sc = d.sc + e;
+    const float *gnew = d.gnext + (size_t)e * d.Pp;
+    const float *gold = d.gprev + (size_t)e * d.Pp;
+    float *rg = d.ringg + ((size_t)e * d.H + sc->head) * d.Pp;    // eval<w_new> has advanced the head
+    float4 gn[UPD_QUADS], go[UPD_QUADS];
+    int pq[UPD_QUADS];
+#pragma unroll
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        pq[i] = seg * UPD_SEG + (i * 256 + threadIdx.x) * 4;
+        if (pq[i] < d.P) {
+            gn[i] = *reinterpret_cast<const float4 *>(gnew + pq[i]);
+            go[i] = *reinterpret_cast<const float4 *>(gold + pq[i]);
+        }
+    }
+    float s_absadjg = 0.f, s_gdiff = 0.f;
+#pragma unroll
+    for (int i = 0; i < UPD_QUADS; ++i) {
+        if (pq[i] >= d.P) continue;
+        const float g1[4] = {gn[i].x, gn[i].y, gn[i].z, gn[i].w};
+        const float g0[4] = {go[i].x, go[i].y, go[i].z, go[i].w};
+        float ag[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ag[j] = ratio_nn(g1[j], g0[j]);
+            if (pq[i] + j < d.P) {
+                s_absadjg += fabsf(ag[j]);
+                s_gdiff += fabsf(g1[j] - g0[j]);
+            } else {
+                ag[j] = 0.f;
+            }
+        }
+        *reinterpret_cast<float4 *>(rg + pq[i]) = make_float4(ag[0], ag[1], ag[2], ag[3]);
+    }
+    __shared__ double red[8 * 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double v0 = warp_sum((double)s_absadjg), v1 = warp_sum((double)s_gdiff);
+    if (lane == 0) { red[warp * 2] = v0; red[warp * 2 + 1] = v1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *out = d.part_r + ((size_t)e * d.nsegU + seg) * 4;
+        for (int i = 0; i < 2; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[w * 2 + i];
+            out[i] = v;
+        }
+    }
+}
+
+// sum |x| of every ring slot after b2e_set_state wrote the rings (ring-only steps rebuild states_sum from these)
+__global__ void __launch_bounds__(256) slot_abs_kernel(Dev d) {
+    const int e = blockIdx.x / d.H, slot = blockIdx.x - e * d.H;
+    const float *rw = d.ringw + ((size_t)e * d.H + slot) * d.Pp, *rg = d.ringg + ((size_t)e * d.H + slot) * d.Pp;
+    double sw = 0.0, sg = 0.0;
+    for (int p = threadIdx.x; p < d.P; p += blockDim.x) { sw += (double)fabsf(rw[p]); sg += (double)fabsf(rg[p]); }
+    __shared__ double red[8];
+    sw = block_sum(sw, red);
+    sg = block_sum(sg, red);
+    if (threadIdx.x == 0) { d.slot_abs[((size_t)e * d.H + slot) * 2] = sw; d.slot_abs[((size_t)e * d.H + slot) * 2 + 1] = sg; }
+}
+
 // info entries that need the streaming kernels' partial sums (states_*, adjusted_grad, grad_diff)
 __global__ void info_finalize_kernel(Dev d, StepArgs a) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= d.E) return;
     const EnvScalars *sc = d.sc + e;
+    const bool ring_only = a.obs == nullptr;
     double absadjg = 0.0, gdiff = 0.0, state = 0.0;
-    for (int s = 0; s < d.nseg; ++s) {
-        const double *in = d.part + ((size_t)e * d.nseg + s) * 4;
-        absadjg += in[0]; gdiff += in[1]; state += in[2];
+    if (ring_only) {
+        for (int s = 0; s < d.nsegU; ++s) {
+            const double *in = d.part_r + ((size_t)e * d.nsegU + s) * 4;
+            absadjg += in[0]; gdiff += in[1];
+        }
+    } else {
+        for (int s = 0; s < d.nseg; ++s) {
+            const double *in = d.part + ((size_t)e * d.nseg + s) * 4;
+            absadjg += in[0]; gdiff += in[1]; state += in[2];
+        }
+    }
+    if (d.slot_abs) {
+        // every step records sum |.| of the two planes it appended; a ring-only step, which never visits
+        // the older slots, adds those up for states_mean / states_sum (multioptlrs.py:119-120)
+        double absaw = 0.0;
+        for (int s = 0; s < d.nsegU; ++s) absaw += d.part_u[((size_t)e * d.nsegU + s) * 4 + 3];
+        double *sa = d.slot_abs + (size_t)e * d.H * 2;
+        sa[sc->head * 2] = absaw;
+        sa[sc->head * 2 + 1] = absadjg;
+        if (ring_only) {
+            for (int h = 0; h < d.H && h < sc->nvalid; ++h) {
+                int slot = sc->head - h;
+                slot += slot < 0 ? d.H : 0;
+                state += sa[slot * 2] + sa[slot * 2 + 1];
+            }
+        }
     }
     double labs = 0.0;
     for (int h = 0; d.col_l >= 0 && h < d.H && h < sc->nvalid; ++h) {
@@ -3195,6 +3290,7 @@ struct b2e_env {
     size_t smem_eval;
     int eval_grid;
     double *part_u;
+    double *part_r, *slot_abs;       // ring-only steps: ring_adjg_kernel's partial sums, per-slot sums of |adjusted x|
     cudaStream_t side;               // the observation kernel runs here (lowest priority) ...
     cudaStream_t hi;                 // ... next to the compute kernel (highest priority)
     cudaEvent_t ev_fork, ev_join;
@@ -3532,6 +3628,13 @@ int launch(b2e_handle h, StepArgs args, void *stream) {
 
 }  // namespace
 
+const void *b2e_dev_view(b2e_handle h, int *ring_ok, int *device) {
+    if (!h) return nullptr;
+    if (ring_ok) *ring_ok = (h->d.split && h->d.env_kind == B2E_ENV_MULTIOPTLRS && h->d.col_w == 0 && h->ringw && h->ringg) ? 1 : 0;
+    if (device) *device = h->cfg.device;
+    return &h->d;
+}
+
 extern "C" {
 
 int b2e_abi_version(void) { return B2E_ABI_VERSION; }
@@ -3587,7 +3690,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
     h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -3647,6 +3750,12 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             !dmalloc((void **)&h->part_u, (size_t)d.E * d.nsegU * 4 * sizeof(double)))
             return bail("b2e_create: cudaMalloc of the split-path buffers failed");
         cudaMemset(h->gnext, 0, EP * 4);
+        if (cfg->env_kind == B2E_ENV_MULTIOPTLRS) {          // ring-only steps (obs_out = NULL)
+            if (!dmalloc((void **)&h->part_r, (size_t)d.E * d.nsegU * 4 * sizeof(double)) ||
+                !dmalloc((void **)&h->slot_abs, (size_t)d.E * d.H * 2 * sizeof(double)))
+                return bail("b2e_create: cudaMalloc of the ring-only buffers failed");
+            cudaMemset(h->slot_abs, 0, (size_t)d.E * d.H * 2 * sizeof(double));
+        }
         if (cudaFuncSetAttribute(mo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)h->smem_obs) != cudaSuccess)
             return bail("b2e_create: observation kernel does not fit (max_history too large)");
@@ -3792,7 +3901,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         if (!ok) return bail("b2e_create: row table: " + err);
     }
     d.X = h->X; d.labels = h->labels; d.targets = h->targets_f;
-    d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part; d.part_u = h->part_u;
+    d.w = h->w; d.gprev = h->gprev; d.gnext = h->gnext; d.part = h->part; d.part_u = h->part_u; d.part_r = h->part_r; d.slot_abs = h->slot_abs;
     d.ringw = h->ringw; d.ringg = h->ringg; d.sc = h->sc; d.w2 = h->w2; d.g2 = h->g2; d.ws = h->ws;
     d.ord = h->ord; d.perm = h->perm; d.perm_stride = d.N; d.row_of_param = h->row_of_param; d.param_of_row = h->param_of_row;
     if (h->use_tc2) {
@@ -3813,7 +3922,7 @@ void b2e_destroy(b2e_handle h) {
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
     cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws);
     b2e_tc2_destroy(h->tc2);
-    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u);
+    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u); cudaFree(h->part_r); cudaFree(h->slot_abs);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -3889,8 +3998,11 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
              double *info_out, void *stream) {
     if (!h) return 1;
     DeviceGuard guard(h->cfg.device);
-    if (!actions || !obs_out || !reward_out || !done_out || !info_out)
+    if (!actions || !reward_out || !done_out || !info_out)
         return fail(h, "b2e_step: null pointer");
+    // obs_out = NULL: ring-only step, the observation rows are not materialised (b200policy.h reads the rings)
+    if (!obs_out && !(h->d.split && h->d.env_kind == B2E_ENV_MULTIOPTLRS && h->slot_abs && !h->fuse_update && h->nchunks <= 1))
+        return fail(h, "b2e_step: obs_out = NULL needs a MultiOptLRs env on the large-problem pipeline");
     if (check_ready(h, batch_idx, batch_cnt)) return 1;
     StepArgs a;
     memset(&a, 0, sizeof(a));
@@ -4030,7 +4142,9 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         h->launches--;
     }
     mark(3);
-    {
+    if (!obs_out) {
+        ring_adjg_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
+    } else {
         const int items = d.nseg * d.E;
         if (h->obs_stages || h->obs_regs) {
             const int grid2 = (items + O2_WARPS - 1) / O2_WARPS;
@@ -4119,6 +4233,7 @@ static int state_io(b2e_handle h, int which, void *user, size_t bytes, void *str
         case B2E_STATE_ADJ_WEIGHTS: case B2E_STATE_ADJ_GRADS: case B2E_STATE_ADJ_LOSSES:
             if (!to_user) set_nvalid_kernel<<<(d.E + 127) / 128, 128, 0, s>>>(d, d.H);
             ring_copy_kernel<<<d.E, 256, 0, s>>>(d, which, (float *)user, to_user);
+            if (!to_user && d.slot_abs && which != B2E_STATE_ADJ_LOSSES) slot_abs_kernel<<<d.E * d.H, 256, 0, s>>>(d);
             break;
         case B2E_STATE_ORDER:
             if (!h->ord) return fail(h, "b2e_get/set_state: no internal index stream");

@@ -58,6 +58,10 @@ struct Dev {
     int ev_X0, ev_X1, ev_W0, ev_W1, ev_XS;   // eval kernel: streamed X / W tile buffers
     int nsegU;
     double *part_u;
+    // ring-only steps (b2e_step with obs_out = NULL): partial sums of ring_adjg_kernel [E][nsegU][4] and the
+    // per-slot sums of |adjusted weights| / |adjusted gradients| [E][H][2] that states_mean / states_sum
+    // are rebuilt from without re-reading the rings
+    double *part_r, *slot_abs;
     // observation layout (utils/utils_env.py:22-44): first column of each key's block or -1
     int col_w, col_l, col_g;
     float *w2, *g2;                  // x_{t-2} planes of the raw History, observation version 2

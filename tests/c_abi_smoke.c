@@ -6,6 +6,7 @@
 
 #include "b200data.h"
 #include "b200env.h"
+#include "b200policy.h"
 
 #define RESOLVE(name)                                        \
     do {                                                     \
@@ -22,6 +23,9 @@ int main(int argc, char **argv) {
     size_t (*rank_workspace)(void);
     int (*column_minmax)(const void *, int, int64_t, int, double *, double *, void *, void *);
     const char *(*data_error)(void);
+    int (*policy_create)(int, int, int, b2p_handle *);
+    const char *(*policy_error)(b2p_handle);
+    b2p_handle policy = NULL;
     if (argc < 2) return 64;
     lib = dlopen(argv[1], RTLD_NOW);
     if (!lib) { fprintf(stderr, "%s\n", dlerror()); return 1; }
@@ -33,6 +37,8 @@ int main(int argc, char **argv) {
     RESOLVE(b2d_last_error); RESOLVE(b2d_resize_nearest); RESOLVE(b2d_minmax_workspace);
     RESOLVE(b2d_column_minmax); RESOLVE(b2d_normalize); RESOLVE(b2d_rank_workspace);
     RESOLVE(b2d_label_ranks); RESOLVE(b2d_onehot);
+    RESOLVE(b2p_create); RESOLVE(b2p_destroy); RESOLVE(b2p_last_error); RESOLVE(b2p_set_weights);
+    RESOLVE(b2p_act); RESOLVE(b2p_act_env);
     *(void **)&abi_version = dlsym(lib, "b2e_abi_version");
     *(void **)&minmax_workspace = dlsym(lib, "b2d_minmax_workspace");
     *(void **)&rank_workspace = dlsym(lib, "b2d_rank_workspace");
@@ -43,6 +49,10 @@ int main(int argc, char **argv) {
     /* argument errors are reported before any CUDA call */
     if (column_minmax(NULL, B2D_U8, 0, 49, NULL, NULL, NULL, NULL) != B2D_EINVAL) return 5;
     if (!strstr(data_error(), "b2d_column_minmax")) return 6;
+    *(void **)&policy_create = dlsym(lib, "b2p_create");
+    *(void **)&policy_error = dlsym(lib, "b2p_last_error");
+    if (policy_create(0, B2P_MAX_OBS_DIM + 1, B2P_TANH_F32, &policy) == 0 || policy != NULL) return 7;
+    if (!strstr(policy_error(NULL), "obs_dim")) return 8;
     printf("c abi ok\n");
     return 0;
 }

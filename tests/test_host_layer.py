@@ -66,7 +66,7 @@ def test_library_exports_every_declared_symbol():
     include = os.path.join(os.path.dirname(__file__), '..', 'include')
     header = ''.join(open(os.path.join(include, name)).read() for name in sorted(os.listdir(include)))
     import re
-    declared = set(re.findall(r'\b(b2[ed]_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(b2[edp]_[a-z_]+)\s*\(', header))
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
