@@ -56,6 +56,7 @@ struct Args {
     const float *obs;                 // dense front end: [rows, obs_dim]
     float *out;
     long long rows, tiles;
+    int units, segs;                  // ring front end: units = envs x segments of an env's tiles
     unsigned long long seed;
     float noise_std, low, high;
     int obs_dim, bulk_ok;
@@ -129,12 +130,15 @@ __device__ __forceinline__ float row_noise(unsigned long long seed, long long ro
     return sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2);
 }
 
-template <bool RING, int TANH>
+// FRONT: 0 = dense observation rows, 1 = rings with max_history 5 (every index a compile-time constant),
+// 2 = rings with any max_history <= 5
+template <int FRONT, int TANH>
 __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constant__ Args a, const __grid_constant__ Dev d) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t obs_full[GROUPS][2];
     __shared__ __align__(8) uint64_t mma_bar[GROUPS];
     __shared__ uint32_t tmem_slot;
+    constexpr bool RING = FRONT != 0;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int g = warp >> 2, wq = warp & 3, gt = tid & 127;          // group, TMEM lane quarter, row of the tile
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -203,54 +207,104 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
             if (gt == 0) mbar_arrive(&obs_full[g][b]);
         }
     };
-    auto load_ring = [&](long long tile, float (&x)[XMAX]) {  // observation row of parameter p of env e from the rings
-        const int e = (int)(tile / tiles_per_env);
-        const int p = (int)(tile - (long long)e * tiles_per_env) * TILE + gt;
-        const EnvScalars *sc = d.sc + e;
-        const int head = sc->head, nvalid = sc->nvalid, H = d.H;
+    // Ring front end.  A CTA owns "units" (env, segment of the env's tiles), u = blockIdx.x + k * gridDim.x,
+    // and its four groups share a unit's tiles round robin: the env's ring position (head, nvalid) and loss
+    // history sit behind a dependent load and are fetched once per unit, not once per tile.  The cursor is
+    // always ONE TILE AHEAD of the tile being computed: load_ring issues the 2H loads of that tile into
+    // registers (raw values) under the current tile's work, ring_row turns them into the observation row
+    // when the tile's turn comes.
+    struct Cursor {
+        long long tile;               // dense: tile index
+        int unit, tp, hi, e, head, nvalid;
+        bool valid;
+        float lv[XMAX / 3];           // adjusted losses newest first (0 beyond nvalid)
+    };
+    auto ring_enter = [&](Cursor &c) {                      // first tile of this group in unit c.unit or a later one
+        for (; c.unit < a.units; c.unit += (int)gridDim.x) {
+            const int e = c.unit / a.segs, sg = c.unit - e * a.segs;
+            const int lo = (int)((long long)sg * tiles_per_env / a.segs), hi = (int)((long long)(sg + 1) * tiles_per_env / a.segs);
+            if (lo + g >= hi) continue;
+            const EnvScalars *sc = d.sc + e;
+            c.e = e; c.tp = lo + g; c.hi = hi; c.head = sc->head; c.nvalid = sc->nvalid; c.valid = true;
+#pragma unroll
+            for (int h = 0; h < XMAX / 3; ++h) {
+                const int H = FRONT == 1 ? 5 : d.H;
+                int slot = c.head - h;
+                slot += slot < 0 ? H : 0;
+                c.lv[h] = (h < H && h < c.nvalid) ? sc->adj_loss[slot] : 0.f;
+            }
+            return;
+        }
+        c.valid = false;
+    };
+    auto advance = [&](Cursor &c) {
+        if (RING) {
+            c.tp += GROUPS;
+            if (c.tp >= c.hi) { c.unit += (int)gridDim.x; ring_enter(c); }
+        } else {
+            c.tile += (long long)gridDim.x * GROUPS;
+            c.valid = c.tile < a.tiles;
+        }
+    };
+    auto load_ring = [&](const Cursor &c, float (&x)[XMAX]) {
+        const int p = c.tp * TILE + gt, H = FRONT == 1 ? 5 : d.H;
         const bool ok = p < d.P;
 #pragma unroll
-        for (int k = 0; k < XMAX; ++k) x[k] = 0.f;
-#pragma unroll
         for (int h = 0; h < XMAX / 3; ++h) {
+            float wv = 0.f, gv = 0.f;
             if (h < H) {
-                int slot = head - h;
+                int slot = c.head - h;
                 slot += slot < 0 ? H : 0;
-                const bool live = ok && h < nvalid;
-                const size_t off = ((size_t)e * H + slot) * d.Pp + p;
-                const float wv = live ? d.ringw[off] : 0.f;
-                const float gv = live ? d.ringg[off] : 0.f;
-                const float lv = h < nvalid ? sc->adj_loss[slot] : 0.f;
-                // unrolled with compile-time h: the three indices are registers, not local memory
-                if (H == 5) { x[h] = clip_m1(wv); x[5 + h] = clip_m1(lv); x[10 + h] = clip_m1(gv); }
-                else {
+                const size_t off = ((size_t)c.e * H + slot) * d.Pp + p;
+                if (ok && h < c.nvalid) { wv = d.ringw[off]; gv = d.ringg[off]; }
+            }
+            x[3 * h] = wv; x[3 * h + 1] = c.lv[h]; x[3 * h + 2] = gv;
+        }
+    };
+    auto ring_row = [&](const float (&raw)[XMAX], float (&x)[XMAX]) {   // [adj_w (H) | adj_L (H) | adj_g (H)], clip, -1
 #pragma unroll
-                    for (int k = 0; k < XMAX; ++k) {
-                        if (k == h) x[k] = clip_m1(wv);
-                        if (k == H + h) x[k] = clip_m1(lv);
-                        if (k == 2 * H + h) x[k] = clip_m1(gv);
-                    }
+        for (int k = 0; k < XMAX; ++k) x[k] = 0.f;
+        if (FRONT == 1) {
+#pragma unroll
+            for (int h = 0; h < 5; ++h) { x[h] = clip_m1(raw[3 * h]); x[5 + h] = clip_m1(raw[3 * h + 1]); x[10 + h] = clip_m1(raw[3 * h + 2]); }
+        } else {
+            const int H = d.H;                               // rare shapes: the row is assembled with selects
+#pragma unroll
+            for (int k = 0; k < XMAX; ++k) {
+                float v = 0.f;
+#pragma unroll
+                for (int h = 0; h < XMAX / 3; ++h) {
+                    v = (k == h && h < H) ? raw[3 * h] : v;
+                    v = (k == H + h && h < H) ? raw[3 * h + 1] : v;
+                    v = (k == 2 * H + h && h < H) ? raw[3 * h + 2] : v;
                 }
+                x[k] = k < 3 * H ? clip_m1(v) : 0.f;
             }
         }
     };
 
-    const long long stride = (long long)gridDim.x * GROUPS;
-    long long tile = (long long)blockIdx.x * GROUPS + g;
+    Cursor c;
+    c.tile = (long long)blockIdx.x * GROUPS + g;
+    c.unit = (int)blockIdx.x;
+    c.valid = c.tile < a.tiles;
+    if (RING) ring_enter(c);
     uint32_t mph = 0;
     float nxt[XMAX];
-    if (tile < a.tiles) {
-        if (RING) load_ring(tile, nxt);
-        else fetch_dense(tile, 0);
+    long long tile = 0;               // the tile being computed: dense index / (env, tile of the env)
+    int cur_e = 0, cur_tp = 0;
+    bool have = c.valid;
+    if (have) {
+        if (RING) { load_ring(c, nxt); cur_e = c.e; cur_tp = c.tp; }
+        else { fetch_dense(c.tile, 0); tile = c.tile; }
+        advance(c);
     }
-    for (int n = 0; tile < a.tiles; tile += stride, ++n) {
+    for (int n = 0; have; ++n) {
         float x[XMAX];
         if (RING) {
-#pragma unroll
-            for (int k = 0; k < XMAX; ++k) x[k] = nxt[k];
+            ring_row(nxt, x);
         } else {
             const int b = n & 1;
-            if (tile + stride < a.tiles) fetch_dense(tile + stride, b ^ 1);
+            if (c.valid) fetch_dense(c.tile, b ^ 1);
             mbar_wait(&obs_full[g][b], (uint32_t)(n >> 1) & 1u);
             const float *st = reinterpret_cast<const float *>(gsm + b * STAGE_BYTES) + gt * od;
             const bool live = tile * TILE + gt < a.rows;
@@ -273,7 +327,11 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
             mma_bf16(tm1, a1d, b1d, idesc, 0u);
             mma_commit(&mma_bar[g]);
         }
-        if (RING && tile + stride < a.tiles) load_ring(tile + stride, nxt);     // in flight under this tile's work
+        const bool have_next = c.valid;
+        const long long next_tile = c.tile;
+        const int next_e = c.e, next_tp = c.tp;
+        if (RING && have_next) load_ring(c, nxt);             // in flight under this tile's work
+        if (have_next) advance(c);
         mbar_wait(&mma_bar[g], mph);
         mph ^= 1u;
         tc_fence_after();
@@ -338,16 +396,16 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
         long long orow;
         bool live;
         if (RING) {
-            const int e = (int)(tile / tiles_per_env);
-            const int p = (int)(tile - (long long)e * tiles_per_env) * TILE + gt;
+            const int p = cur_tp * TILE + gt;
             live = p < d.P;
-            orow = (long long)e * d.P + (live ? (d.row_lex ? d.row_of_param[p] : p) : 0);
+            orow = (long long)cur_e * d.P + (live ? (d.row_lex ? d.row_of_param[p] : p) : 0);
         } else {
             orow = tile * TILE + gt;
             live = orow < a.rows;
         }
         if (a.noise_std != 0.f) mean = fmaf(a.noise_std, row_noise(a.seed, orow), mean);
         if (live) a.out[orow] = fminf(fmaxf(mean, a.low), a.high);
+        have = have_next; tile = next_tile; cur_e = next_e; cur_tp = next_tp;
     }
     tc_fence_before();
     __syncthreads();
@@ -383,19 +441,21 @@ struct PolicyDeviceGuard {
     ~PolicyDeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 
-template <bool RING>
+template <int FRONT>
 cudaError_t launch_policy(int tanh_mode, int grid, cudaStream_t cs, const pol::Args &a, const Dev &d) {
     switch (tanh_mode) {
-        case 2: pol::policy_kernel<RING, 2><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
-        case 1: pol::policy_kernel<RING, 1><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
-        default: pol::policy_kernel<RING, 0><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
+        case 2: pol::policy_kernel<FRONT, 2><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
+        case 1: pol::policy_kernel<FRONT, 1><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
+        default: pol::policy_kernel<FRONT, 0><<<grid, pol::THREADS, pol::SMEM_BYTES, cs>>>(a, d); break;
     }
     return cudaGetLastError();
 }
 
-template <bool RING, int TANH>
+template <int FRONT>
 bool set_policy_smem() {
-    return cudaFuncSetAttribute(pol::policy_kernel<RING, TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES) == cudaSuccess;
+    return cudaFuncSetAttribute(pol::policy_kernel<FRONT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(pol::policy_kernel<FRONT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES) == cudaSuccess &&
+           cudaFuncSetAttribute(pol::policy_kernel<FRONT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::SMEM_BYTES) == cudaSuccess;
 }
 
 void fill_weights(const b2p_policy *h, pol::Args &a) {
@@ -420,8 +480,7 @@ int b2p_create(int device, int obs_dim, int tanh_mode, b2p_handle *out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return pfail(nullptr, "b2p_create: no such CUDA device");
     if (prop.major != 10) return pfail(nullptr, "b2p_create: the policy kernel needs an sm_100 GPU (tcgen05); there is no fallback");
-    if (!(set_policy_smem<false, 0>() && set_policy_smem<false, 1>() && set_policy_smem<false, 2>() &&
-          set_policy_smem<true, 0>() && set_policy_smem<true, 1>() && set_policy_smem<true, 2>()))
+    if (!(set_policy_smem<0>() && set_policy_smem<1>() && set_policy_smem<2>()))
         return pfail(nullptr, "b2p_create: the policy kernel does not fit shared memory");
     b2p_policy *h = new (std::nothrow) b2p_policy();
     if (!h) return pfail(nullptr, "b2p_create: out of host memory");
@@ -479,7 +538,7 @@ int b2p_act(b2p_handle h, const float *obs, int64_t rows, float *actions_out, fl
     memset(&d, 0, sizeof(d));
     const long long want = (a.tiles + pol::GROUPS - 1) / pol::GROUPS;
     const int grid = (int)(want < h->num_sms ? want : h->num_sms);
-    const cudaError_t err = launch_policy<false>(h->tanh_mode, grid, (cudaStream_t)stream, a, d);
+    const cudaError_t err = launch_policy<0>(h->tanh_mode, grid, (cudaStream_t)stream, a, d);
     if (err != cudaSuccess) return pfail(h, std::string("b2p_act: ") + cudaGetErrorString(err));
     return 0;
 }
@@ -500,11 +559,18 @@ int b2p_act_env(b2p_handle h, b2e_handle env, float *actions_out, float noise_st
     fill_weights(h, a);
     a.out = actions_out;
     a.rows = (long long)dv->E * dv->P;
-    a.tiles = (long long)dv->E * ((dv->P + pol::TILE - 1) / pol::TILE);
+    const int tiles_per_env = (dv->P + pol::TILE - 1) / pol::TILE;
+    a.tiles = (long long)dv->E * tiles_per_env;
+    // few envs: split every env's tiles into segments so that all SMs have work (>= 4 rounds of tiles per group and segment)
+    int segs = (3 * h->num_sms + dv->E - 1) / dv->E;
+    const int max_segs = tiles_per_env / (4 * pol::GROUPS);
+    segs = segs > max_segs ? max_segs : segs;
+    a.segs = segs < 1 ? 1 : segs;
+    a.units = dv->E * a.segs;
     a.seed = seed; a.noise_std = noise_std; a.low = low; a.high = high;
-    const long long want = (a.tiles + pol::GROUPS - 1) / pol::GROUPS;
-    const int grid = (int)(want < h->num_sms ? want : h->num_sms);
-    const cudaError_t err = launch_policy<true>(h->tanh_mode, grid, (cudaStream_t)stream, a, *dv);
+    const int grid = a.units < h->num_sms ? a.units : h->num_sms;
+    const cudaError_t err = dv->H == 5 ? launch_policy<1>(h->tanh_mode, grid, (cudaStream_t)stream, a, *dv)
+                                      : launch_policy<2>(h->tanh_mode, grid, (cudaStream_t)stream, a, *dv);
     if (err != cudaSuccess) return pfail(h, std::string("b2p_act_env: ") + cudaGetErrorString(err));
     return 0;
 }
