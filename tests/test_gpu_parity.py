@@ -128,6 +128,107 @@ def unclipped_obs_err(obs, want, obs_version):
     return err, (2e-3 if obs_version == 2 else 1e-4)
 
 
+class NoiseAllowance:
+    """Per-entry error allowance of MultiOptimize observation rows: what the bars of the INPUTS imply.
+
+    Losses, gradients and weights are held to RTOL of their natural scale elsewhere in this file; an
+    observation entry is a ratio of two of them (utils/utils_env.py:126-164), so where the denominator
+    is small next to that scale the same input error is a large output error (a gradient component that
+    happens to vanish).  The allowance of a new entry is |f(x + d) - f(x)| for input perturbations d of
+    the size of the input bars, evaluated with the oracle's own ``observation_ratios``; it then moves
+    through the adjusted History with the entry (same key order / depth as the oracle's layout)."""
+
+    def __init__(self, ref):
+        self.ref = ref
+        e, p, h = ref.num_envs, ref.num_params, ref.depth
+        self.w, self.g, self.l = np.zeros((h, e, p)), np.zeros((h, e, p)), np.zeros((h, e))
+
+    def reset(self, env_mask):
+        self.w[:, env_mask] = 0
+        self.g[:, env_mask] = 0
+        self.l[:, env_mask] = 0
+
+    def step(self, obs_version):
+        ref = self.ref
+        base = orc.observation_ratios(ref.raw_l, ref.raw_g, ref.raw_w, obs_version)
+        dg = RTOL * np.abs(ref.raw_g[:3]).mean(axis=2, keepdims=True)
+        dw = RTOL * np.abs(ref.raw_w[:3]).mean(axis=2, keepdims=True)
+        dl = RTOL * np.abs(ref.raw_l[:3])
+        worst = [np.zeros_like(b, dtype=np.float64) for b in base]
+        for signs in ((1, -1, 1), (1, 1, -1), (-1, -1, 1), (1, 0, 0), (0, 1, 0), (0, 0, 1)):
+            sg = np.array(signs, np.float64)
+            pert_l, pert_g, pert_w = ref.raw_l.copy(), ref.raw_g.copy(), ref.raw_w.copy()
+            pert_l[:3] += sg[:, None] * dl
+            pert_g[:3] += sg[:, None, None] * dg
+            pert_w[:3] += sg[:, None, None] * dw
+            with np.errstate(all='ignore'):
+                out = orc.observation_ratios(pert_l, pert_g, pert_w, obs_version)
+                worst = [np.fmax(wst, np.nan_to_num(np.abs(o - b), posinf=1e300)) for wst, o, b in zip(worst, out, base)]
+        # a denominator within a few input bars of zero: the perturbed interval contains a pole, no finite
+        # allowance (EXACT zeros are structural -- zero-initialised biases, dead relu units -- and exact on
+        # both sides: nan_to_num(x/0) is compared by unclipped_obs_err)
+        with np.errstate(all='ignore'):
+            g, w = ref.raw_g, ref.raw_w
+            if obs_version == 3:
+                poles = ((np.abs(w[1]) <= 4 * dw[1]) & (w[1] != 0), (np.abs(g[1]) <= 4 * dg[1]) & (g[1] != 0))
+            elif obs_version == 2:
+                poles = (np.abs(w[0] - w[1]) + 1e-8 <= 4 * (dw[0] + dw[1]), np.abs(g[1] - g[2]) + 1e-3 <= 4 * (dg[1] + dg[2]))
+            else:
+                poles = (np.abs(w[1]) + 1e-3 <= 4 * dw[1], (np.abs(g[1]) + 1e-3 <= 4 * dg[1]) & (obs_version == 0))
+        worst[1] = np.where(poles[0], np.inf, worst[1])
+        worst[2] = np.where(poles[1], np.inf, worst[2])
+        for ring, new in ((self.l, worst[0]), (self.w, worst[1]), (self.g, worst[2])):
+            ring[1:] = ring[:-1].copy()
+            ring[0] = new
+
+    def matrix(self):
+        """[E, P, obs_dim] in the oracle's observation layout."""
+        ref, cols = self.ref, []
+        for key in ref.keys:
+            if key == 'weights':
+                cols.append(self.w.transpose(1, 2, 0))
+            elif key == 'gradients':
+                cols.append(self.g.transpose(1, 2, 0))
+            else:
+                cols.append(np.broadcast_to(self.l.T[:, None, :], (ref.num_envs, ref.num_params, ref.depth)))
+        return np.concatenate(cols, axis=2)
+
+
+ALL_INFO_KEYS = ('loss', 'batch_loss', 'weights_mean', 'weights_sum', 'actions_mean', 'actions_std', 'states_mean',
+                 'states_sum', 'grads_mean', 'grads_sum', 'loss_mean', 'adjusted_loss', 'adjusted_grad', 'grad_diff')
+
+
+def check_unclipped_info(got, want_of, obs_version, g_abs_sum, num_params, tag, extra_atol=None):
+    """All 14 info statistics (multioptlrs.py:111-127 / multioptimize.py:130-152) of a MultiOptimize-style step.
+    ``g_abs_sum`` [E]: sum |g| over the raw gradient History, the scale of the signed gradient sums."""
+    loose = reward_tol(obs_version)
+    for key in ALL_INFO_KEYS:
+        have, want = np.asarray(got[key], np.float64), np.asarray(want_of(key), np.float64)
+        msg = str(tag + (key,))
+        if key == 'loss':                                   # None unless terminal
+            assert np.array_equal(np.isnan(have), np.isnan(want)), msg
+            ok = ~np.isnan(want)
+            np.testing.assert_allclose(have[ok], want[ok], rtol=2e-4, atol=1e-6, err_msg=msg)
+        elif key in ('grads_mean', 'grads_sum'):
+            scale = g_abs_sum / (5 * num_params if key == 'grads_mean' else 1)
+            assert np.all(np.abs(have - want) <= 2 * RTOL * scale + 1e-12), (msg, have, want, scale)
+        elif key in ('states_mean', 'states_sum', 'adjusted_grad'):
+            # sums over un-clipped ratios: one x/0 -> nan_to_num is float64 max in the reference and float32 max
+            # on the device (SURVEY 8a), and a vanishing denominator makes the sum as ill conditioned as its
+            # largest term -- compared where the statistic is moderate
+            fine = np.abs(want) < (1e3 if key != 'states_sum' else 1e3 * num_params)
+            tol = loose if obs_version in (2, 3) else dict(rtol=1e-3, atol=1e-6)
+            slack = tol['atol'] + tol['rtol'] * np.abs(want)
+            if extra_atol is not None:                      # what the input bars allow for the summed entries
+                slack = slack + extra_atol[key]
+            assert np.all(np.abs(have - want)[fine] <= slack[fine]), (msg, have, want, slack)
+            _stat(tag + (key,), max_over_bar=(np.abs(have[fine] - want[fine]) / np.maximum(np.abs(want[fine]), 1e-6)).max()
+                  if fine.any() else 0.0, frac=float(fine.mean()))
+        else:
+            tol = loose if key == 'adjusted_loss' else dict(rtol=2e-4, atol=1e-6)
+            np.testing.assert_allclose(have, want, err_msg=msg, **tol)
+
+
 def reward_tol(obs_version):
     return dict(rtol=5e-3, atol=5e-3) if obs_version == 2 else dict(rtol=1e-4, atol=1e-4)
 
@@ -400,6 +501,9 @@ def test_sampled_env_parity_at_baseline_sizes(name):
     env.close()
 
 
+GOLDEN_CAP = 3.0           # all-entries cap of the golden replays, in units of the 97-99 % bar
+
+
 @pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_golden_reference_runs_on_device(path):
     """The fixtures recorded from the reference's own env code, replayed on the GPU with the
@@ -461,18 +565,20 @@ def test_golden_reference_runs_on_device(path):
             obs_ver = kwargs['observation_version']
             err, bar = unclipped_obs_err(obs_np, want, obs_ver)
             _stat(('golden', os.path.basename(path), t), max_over_bar=err.max() / bar, frac=np.mean(err <= bar))
-            assert np.mean(err <= bar) > 0.97, (t, float(np.mean(err <= bar)))
+            assert np.mean(err <= bar) > 0.99, (t, float(np.mean(err <= bar)))
+            assert err.max() <= GOLDEN_CAP * bar, (t, float(err.max()))          # EVERY entry (worst measured: 1.32 bar)
             np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], **reward_tol(obs_ver))
             got = env.info_dict(info)
-            for key in ('batch_loss', 'weights_mean', 'weights_sum', 'actions_mean', 'actions_std',
-                        'loss_mean', 'adjusted_loss', 'grad_diff'):
-                tol = reward_tol(obs_ver) if key == 'adjusted_loss' else dict(rtol=2e-4, atol=1e-5)
-                np.testing.assert_allclose(got[key], fix['info_' + key][t],
-                                           err_msg='%s step %d' % (key, t), **tol)
+            # info of the step is recorded per agent row (optvecenv.py:43-45): env e = row e * P
+            g_abs = 5.0 * np.abs(env.get_state('grad_prev').cpu().numpy().astype(np.float64)).sum(axis=1)
+            check_unclipped_info(got, lambda key: fix['info_' + key][t].reshape(num_envs, -1)[:, 0] if
+                                 fix['info_' + key][t].size == num_envs * num_params else fix['info_' + key][t],
+                                 obs_ver, g_abs, num_params, ('golden', os.path.basename(path), t))
         else:
             err = np.abs(obs_np - want) / np.maximum(1.0, np.abs(want + 1))
             _stat(('golden', os.path.basename(path), t), max_over_bar=err.max() / 1e-4, frac=np.mean(err <= 1e-4))
-            assert np.mean(err <= 1e-4) > 0.97, (t, float(np.mean(err <= 1e-4)))
+            assert np.mean(err <= 1e-4) > 0.98, (t, float(np.mean(err <= 1e-4)))
+            assert err.max() <= GOLDEN_CAP * 1e-4, (t, float(err.max()))         # EVERY entry (worst measured: 1.26e-4)
             np.testing.assert_allclose(np.repeat(rew_np, num_params), fix['rewards'][t], rtol=1e-4, atol=1e-4)
         clipped_ok += 1
     assert clipped_ok == fix['actions'].shape[0]
@@ -509,6 +615,8 @@ def test_multioptimize_trajectory_matches_oracle(name, hist_version, obs_version
     obs = env.reset(init_params=init).cpu().numpy()
     want = ref.reset(init_params=init)
     assert np.array_equal(obs, want.astype(np.float32)) and not obs.any()
+    noise = NoiseAllowance(ref.env)
+    perm = orc.lexicographic_rows(num_params)
     for t in range(2 * max_batches + 2):
         actions = rng.uniform(-20, 20, size=env.num_rows).astype(np.float32)   # deltas up to 2e-2
         init = np.stack([orc.glorot_uniform_init(spec, rng) for _ in range(num_envs)])
@@ -525,14 +633,25 @@ def test_multioptimize_trajectory_matches_oracle(name, hist_version, obs_version
         assert done_np.all() == ((t + 1) % max_batches == 0), tag
         err, bar = unclipped_obs_err(obs_np, want_obs, obs_version)
         _stat(('multioptimize',) + tag, max_over_bar=err.max() / bar, frac=np.mean(err <= bar), median=np.median(err))
-        assert np.mean(err <= bar) > 0.97, (tag, float(np.mean(err <= bar)))
+        assert np.mean(err <= bar) > 0.99, (tag, float(np.mean(err <= bar)))
         assert np.median(err) <= (20 if obs_version == 2 else 1) * RTOL, (tag, float(np.median(err)))
+        # EVERY entry: the bar, or what the input bars allow for that entry (ill-conditioned ratios)
+        noise.step(obs_version)                              # the step's own state: what its info statistics sum
+        allow = noise.matrix()
+        info_allow = {'states_sum': allow.sum(axis=(1, 2)), 'states_mean': allow.mean(axis=(1, 2)),
+                      'adjusted_grad': noise.g[0].mean(axis=1)}           # inf where an entry sits on a pole
+        if done_np.any():                                    # the returned rows are the reset observation
+            noise.reset(done_np)
+            allow = noise.matrix()
+        allow_rows = allow[:, perm].reshape(obs_np.shape) / np.maximum(1.0, np.abs(want_obs))
+        assert np.mean(np.isinf(allow_rows)) < 5e-3, (tag, float(np.mean(np.isinf(allow_rows))))   # poles are rare
+        over = err - (bar + allow_rows)
+        _stat(('multioptimize-all',) + tag, max_over_bar=float((err / (bar + allow_rows)).max()), frac=float(np.mean(over <= 0)))
+        assert np.all(over <= 0), (tag, float(over.max()), float(err.max()))
         np.testing.assert_allclose(np.repeat(rew_np, num_params), want_rew, err_msg=str(tag),
                                    **reward_tol(obs_version))
-        for key in ('batch_loss', 'weights_mean', 'weights_sum', 'actions_mean', 'actions_std',
-                    'loss_mean', 'adjusted_loss', 'grad_diff'):
-            tol = reward_tol(obs_version) if key == 'adjusted_loss' else dict(rtol=2e-4, atol=1e-6)
-            np.testing.assert_allclose(got[key], want_info[key], err_msg=str(tag + (key,)), **tol)
+        g_abs = np.abs(ref.env.raw_g).sum(axis=(0, 2))
+        check_unclipped_info(got, lambda key: want_info[key], obs_version, g_abs, num_params, tag, info_allow)
     env.close()
 
 
