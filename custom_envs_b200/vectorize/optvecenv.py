@@ -442,6 +442,11 @@ class OptVecEnv(VecEnv):
     def close(self):
         if self.closed:
             return
+        if self.is_device_backed:
+            # the reference's worker closes its env chain (concurrentvecenv.py:45-47): a Monitor writes the
+            # episodes it still holds (chunk_size > 1) from its close()
+            for env in self._chains:
+                env.close()
         self._impl.close()
         self.closed = True
 

@@ -420,3 +420,129 @@ def test_step_replayed_from_a_cuda_graph_equals_eager_steps(shape):
     assert torch.equal(graphed.get_state('params'), eager.get_state('params'))
     eager.close()
     graphed.close()
+
+
+class _RunnerStandIn:
+    """The slice of stable-baselines' on-policy algorithms the reference scripts exercise (PPO2 / A2C
+    ``learn`` and ``predict``; stable_baselines/ppo2/ppo2.py Runner.run): n_steps of
+    ``env.step(actions)`` with actions [num_envs, 1], rollout lists that keep every step's arrays WITHOUT
+    copying them, the episode-info buffer fed from ``info.get('episode')``, and the ``callback(locals,
+    globals)`` hook.  No learning: the scripts' contract with the env is what is under test."""
+
+    def __init__(self, policy, env, gamma=0.99, learning_rate=1e-3, verbose=0, nminibatches=4, n_steps=4):
+        assert env.num_envs % nminibatches == 0          # ppo2.py: n_batch % nminibatches
+        self.env, self.n_steps = env, n_steps
+        self.observation_space, self.action_space = env.observation_space, env.action_space
+        self.rng = np.random.RandomState(0)
+        self.ep_infos, self.rollouts = [], []
+
+    def predict(self, observation, state=None, mask=None, deterministic=False):
+        observation = np.asarray(observation).reshape((-1,) + self.observation_space.shape)
+        assert observation.shape[0] == self.env.num_envs
+        actions = self.rng.uniform(0.0, 2.0, size=(self.env.num_envs,) + self.action_space.shape)
+        return np.clip(actions, self.action_space.low, self.action_space.high).astype(np.float32), None
+
+    def learn(self, total_timesteps, callback=None):
+        env = self.env
+        obs = np.zeros((env.num_envs,) + self.observation_space.shape, dtype=self.observation_space.dtype)
+        obs[:] = env.reset()
+        dones = [False] * env.num_envs
+        for update in range(1, total_timesteps // (env.num_envs * self.n_steps) + 1):
+            mb_obs, mb_rewards, mb_dones = [], [], []
+            for _ in range(self.n_steps):
+                actions, _ = self.predict(obs)
+                mb_obs.append(obs.copy())
+                mb_dones.append(dones)
+                obs[:], rewards, dones, infos = env.step(actions)
+                for info in infos:
+                    maybe = info.get('episode')
+                    if maybe:
+                        self.ep_infos.append(maybe)
+                mb_rewards.append(rewards)
+            self.rollouts.append((np.asarray(mb_obs), np.asarray(mb_rewards), np.asarray(mb_dones[1:] + [dones])))
+            if callback is not None and callback(locals(), globals()) is False:
+                break
+        return self
+
+
+def test_script_call_sites_of_survey_8b(tmp_path):
+    """SURVEY 8b "who calls it", one call site after the other, against the device-backed classes reached
+    through the reference's own module paths (the scripts themselves need stable-baselines / TF / optuna,
+    absent here; ``_RunnerStandIn`` restates the runner's side of the contract):
+
+    * run_multiagent_exp_single.py:30-49   OptVecEnv(envs), nminibatches=dummy_env.num_envs, learn, close
+    * search_optimize_hyperparam.py:27-62, 95-112   Monitor(partial(gym.make, ...), path, info_keywords, chunk_size),
+      dummy_env.agent_no_list[0], env_method('get_episode_rewards') from the learn callback
+    * eval_multiexp.py:70-92   gym.make(env_name, **kwargs), states = vec_env.reset(), model.predict(states),
+      rewards[0], infos[0] extended in place by the caller
+    * play_optimize.py:79-98   reset / predict / step until any(dones), close (twice: the finally block)
+    * compile_exp.py:8-28      the .mon.csv the Monitor leaves behind"""
+    from custom_envs.vectorize.optvecenv import OptVecEnv
+    from custom_envs.utils.utils_logging import Monitor
+    from custom_envs import load_data
+    import custom_envs_b200.compat as compat
+    gym_make = compat.make                                    # `gym.make` of the scripts (stand-in registry or real gym)
+    data = load_data('iris', 32)
+    kwargs = dict(problem='nn', max_batches=6, problem_kwargs=dict(layers=(), data_set=data))
+    keys = ('loss', 'actions_mean', 'weights_mean', 'actions_std', 'states_mean', 'grads_mean')
+    log_path = str(tmp_path / 'monitor_{:d}')
+    wrapped_envs = [partial(Monitor, partial(gym_make, 'MultiOptLRs-v0', **kwargs), log_path.format(i),
+                            info_keywords=keys, chunk_size=5) for i in range(2)]
+
+    # ---- search_optimize_hyperparam.py / run_multiagent_exp_single.py: train
+    dummy_env = OptVecEnv(wrapped_envs)
+    assert dummy_env.is_device_backed
+    model = _RunnerStandIn('MlpPolicy', dummy_env, gamma=0.99, learning_rate=1e-3, verbose=1,
+                           nminibatches=dummy_env.num_envs)
+    assert dummy_env.num_envs == 30 and dummy_env.agent_no_list[0] == 15
+    timesteps = 20 * dummy_env.agent_no_list[0] * 2           # total_timesteps * agent_no_list[0], two envs
+    totals = []
+
+    def get_total_reward(environment):                        # search_optimize_hyperparam.py:27-33
+        return sum(sum(r) for r in environment.env_method('get_episode_rewards'))
+
+    def callback(local_vars, global_vars):
+        totals.append(get_total_reward(local_vars['self'].env))
+
+    model.learn(total_timesteps=timesteps, callback=callback)
+    assert len(model.rollouts) == 5 and len(totals) == 5      # 600 timesteps / (30 rows x 4 steps)
+    # 20 steps at max_batches = 6: three finished episodes per env, each reported once per agent row
+    assert len(model.ep_infos) == 20 * 30 and all(set(e) >= {'r', 'l'} for e in model.ep_infos)
+    assert totals[-1] != 0 and totals == sorted(totals, key=lambda v: totals.index(v))
+    for mb_obs, mb_rewards, mb_dones in model.rollouts:      # kept arrays were not overwritten by later steps
+        assert mb_obs.shape == (4, 30, 15) and mb_rewards.shape == (4, 30) and mb_dones.shape == (4, 30)
+        assert len({tuple(r) for r in mb_rewards}) == 4       # four distinct steps, not four aliases of the last
+    dummy_env.close()
+    dummy_env.close()                                         # idempotent (concurrentvecenv.py:112-122)
+    frame = pd.read_csv(log_path.format(0) + '.mon.csv')      # compile_exp.py / eval_csv.py read these
+    assert len(frame) == 3 and set(keys) | {'r', 'l', 't'} <= set(frame.columns) and list(frame['l']) == [6, 6, 6]
+
+    # ---- eval_multiexp.py:70-92: one env, the caller extends infos[0]
+    env = partial(gym_make, 'MultiOptLRs-v0', **dict(kwargs, max_batches=4))
+    vec_env = OptVecEnv([env])
+    model = _RunnerStandIn('MlpPolicy', vec_env, nminibatches=1)
+    states = vec_env.reset()
+    info_list, cumulative_reward = [], 0
+    for step in range(6):
+        actions = model.predict(states, deterministic=False)[0]
+        states, rewards, _, infos = vec_env.step(actions)
+        cumulative_reward = cumulative_reward + rewards[0]
+        info = infos[0]
+        info['step'] = step
+        info['cumulative_reward'] = cumulative_reward
+        info_list.append(info)
+    assert [i['step'] for i in info_list] == list(range(6))   # each step handed out its own dict
+    assert all(set(orc.INFO_KEYS) <= set(i) for i in info_list)
+    assert [i['loss'] is not None for i in info_list] == [False, False, False, True, False, False]
+    assert np.isfinite(cumulative_reward)
+
+    # ---- play_optimize.py:79-98: until any(dones)
+    observations = vec_env.reset()
+    done, steps = False, 0
+    while not done:
+        action = model.predict(observations)
+        observations, rewards, dones, infos = vec_env.step(action[0])
+        done = any(dones)
+        steps += 1
+    assert steps == 4 and np.all(observations == -1)          # the auto-reset observation (concurrentvecenv.py:32-38)
+    vec_env.close()
