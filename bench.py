@@ -327,6 +327,7 @@ def gpu_arm(args):
         sampler.start()                       # nvidia-smi needs ~1 s to produce its first line
     for i in range(max(args.warmup, 3)):
         env.step(actions[i & 1])
+    env.done.sum()                            # load torch's reduction kernel now: the timed window calls it once
     barrier()
     if rank == 0:
         deadline = time.time() + 3.0
@@ -341,9 +342,11 @@ def gpu_arm(args):
     launches0 = env.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     done_total = 0
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     start.record()
     for i in range(args.steps):
         env.step(actions[i & 1])
+        marks[i].record()                            # per-step profile of the window (read after it)
         if i == reset_at:
             done_total = env.done.sum()              # device tensor, read after the timed region
     stop.record()
@@ -351,6 +354,7 @@ def gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = env.launch_count - launches0
     ms = start.elapsed_time(stop)
+    step_ms = [a.elapsed_time(b) for a, b in zip([start] + marks[:-1], marks)]
     done_total = int(done_total.item()) if torch.is_tensor(done_total) else 0
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -451,6 +455,9 @@ def gpu_arm(args):
                              % (BYTES_PER_ENV_STEP * envs / 1e9),
                        'episode_end_in_window': {'timed_step': reset_at, 'envs_done': done_total,
                                                  'note': 'every env of rank 0 reaches max_batches there and is auto-reset'},
+                       'step_ms_in_window': {'median': float(np.median(step_ms)), 'min': float(min(step_ms)),
+                                             'max': float(max(step_ms)), 'slowest_step': int(np.argmax(step_ms)),
+                                             'note': 'the slowest step is the one that ends every episode and re-initialises the envs'},
                        'full_reset_ms': reset_ms,
                        'reset_amortised_ms_per_step': {'at_400_steps': reset_ms / 400, 'at_100_steps': reset_ms / 100},
                        'obs_tolerance': 'observations: 1e-5 relative on >= 98 % of the well-conditioned entries, '

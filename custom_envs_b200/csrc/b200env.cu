@@ -2729,6 +2729,125 @@ __global__ void info_finalize_kernel(Dev d, StepArgs a) {
     info[13] = gdiff / P;
 }
 
+
+// =========================================================================================
+// Reset pipeline of the tcgen05 path (MultiOptLRs, BASELINE config 4 / 5): base_reset
+// (envs/multioptlrs.py:66-78) as
+//   reset_list_kernel    : the envs to reset (mask / done flags, or all), ascending, + their count
+//   reset_prepare_kernel : reshuffle (optimize_nn.py:114-120), cursor 0, fresh parameters
+//   tc2 eval kernel      : loss and gradient of the listed envs at the fresh parameters (b200tc.cu)
+//   reset_finish_kernel  : histories / counters, the raw-history gradient sum, the all -1 observation rows
+// instead of the one-CTA-per-SM fused kernel in reset mode (10.4 ms for 4096 envs; this takes ~3 ms).  With no env
+// to reset (the usual auto-reset launch of a step) every kernel finds an empty list and returns.
+// =========================================================================================
+__global__ void __launch_bounds__(1024) reset_list_kernel(const unsigned char *mask, int E, int *list, int *count) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int e0 = 0; e0 < E; e0 += 1024) {
+        const int e = e0 + threadIdx.x;
+        const bool flag = e < E && (!mask || mask[e]);
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (flag) list[off + __popc(ballot & ((1u << lane) - 1u))] = e;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void __launch_bounds__(256) reset_prepare_kernel(const __grid_constant__ Dev d, const __grid_constant__ StepArgs a) {
+    const int n = *a.env_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = a.env_list[i];
+        EnvScalars *sc = d.sc + e;
+        if (d.index_mode == B2E_INDEX_INTERNAL) {
+            // InMemoryDataSet.on_epoch_end (shuffle_order) with eight independent gathers in flight per thread
+            const int sel = sc->ord_sel;
+            const int *src = order_ptr(d, e, sel);
+            int *dst = d.ord + ((size_t)(sel ^ 1) * d.E + e) * d.N;
+            const int *pm = d.perm + (size_t)e * d.perm_stride;
+            if ((d.N & 3) == 0 && (d.perm_stride & 3) == 0) {
+                const int nq = d.N >> 2;
+                for (int q = threadIdx.x; q < nq; q += 2 * blockDim.x) {
+                    const int q2 = q + blockDim.x;
+                    const int4 a4 = reinterpret_cast<const int4 *>(pm)[q];
+                    const int4 b4 = q2 < nq ? reinterpret_cast<const int4 *>(pm)[q2] : make_int4(0, 0, 0, 0);
+                    const int4 ra = make_int4(src[a4.x], src[a4.y], src[a4.z], src[a4.w]);
+                    const int4 rb = make_int4(src[b4.x], src[b4.y], src[b4.z], src[b4.w]);
+                    reinterpret_cast<int4 *>(dst)[q] = ra;
+                    if (q2 < nq) reinterpret_cast<int4 *>(dst)[q2] = rb;
+                }
+            } else {
+                for (int i = threadIdx.x; i < d.N; i += blockDim.x) dst[i] = src[pm[i]];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { sc->ord_sel = sel ^ 1; sc->cursor = 0; }
+            __syncthreads();
+        }
+        const int episode = sc->episode;
+        float *wE = d.w + (size_t)e * d.Pp;
+        for (int p = threadIdx.x; p < d.Pp; p += blockDim.x) {
+            float v = 0.f;
+            if (p < d.P) {
+                if (a.init_params) v = a.init_params[(size_t)e * d.P + p];
+                else if (p < d.P1) v = glorot(d.seed, e, episode, p, d.lim1);
+                else if (d.hidden && p >= d.P1 + d.N1 && p < d.P1 + d.N1 + d.N1 * d.C) v = glorot(d.seed, e, episode, p, d.lim2);
+            }
+            wE[p] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) reset_finish_kernel(const __grid_constant__ Dev d, const __grid_constant__ StepArgs a) {
+    __shared__ double red[8];
+    const int n = *a.env_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int e = a.env_list[i];
+        EnvScalars *sc = d.sc + e;
+        const float *gE = d.gprev + (size_t)e * d.Pp;           // the eval kernel left the reset gradient here
+        double gs = 0.0;
+        for (int p = threadIdx.x; p < d.P; p += blockDim.x) gs += (double)gE[p];
+        gs = block_sum(gs, red);
+        if (threadIdx.x == 0) {
+            const float loss = a.loss_out[e];
+            for (int k = 0; k < RAW_DEPTH; ++k) { sc->raw_loss[k] = 0.f; sc->raw_gsum[k] = 0.0; }   // multioptlrs.py:69
+            for (int k = 0; k < B2E_MAX_HISTORY; ++k) sc->adj_loss[k] = 0.f;
+            sc->raw_pos = 0;
+            sc->raw_loss[0] = loss;
+            sc->raw_gsum[0] = gs;
+            sc->loss_prev = loss;
+            sc->head = d.H - 1;
+            sc->nvalid = 0;
+            sc->step = 0;
+            sc->episode = sc->episode + 1;
+        }
+        if (a.obs) {                                            // clip(0) - 1 = -1 in every column (multioptlrs.py:70-78)
+            float *o = a.obs + (size_t)e * d.P * d.OD;
+            const size_t total = (size_t)d.P * d.OD;
+            const size_t head = min(total, (size_t)((4 - ((reinterpret_cast<uintptr_t>(o) >> 2) & 3)) & 3));
+            const size_t quads = (total - head) >> 2;
+            if (threadIdx.x < head) o[threadIdx.x] = -1.0f;
+            float4 *o4 = reinterpret_cast<float4 *>(o + head);
+            const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+            for (size_t q = threadIdx.x; q < quads; q += blockDim.x) o4[q] = m1;
+            for (size_t t = head + (quads << 2) + threadIdx.x; t < total; t += blockDim.x) o[t] = -1.0f;
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- MultiOptimize
 // envs/multioptimize.py:90-154 as a pipeline for every problem size:
 //   mo_update_kernel : w_t = w_{t-1} - delta(a); adjusted-weight ring; raw weight planes
@@ -3290,6 +3409,9 @@ struct b2e_env {
     size_t smem_eval;
     int eval_grid;
     double *part_u;
+    int *reset_list, *reset_count;   // reset pipeline of the tcgen05 path: work list, its length, losses of the reset evals
+    float *reset_loss;
+    bool reset_pipeline;
     double *part_r, *slot_abs;       // ring-only steps: ring_adjg_kernel's partial sums, per-slot sums of |adjusted x|
     cudaStream_t side;               // the observation kernel runs here (lowest priority) ...
     cudaStream_t hi;                 // ... next to the compute kernel (highest priority)
@@ -3604,7 +3726,26 @@ int configure(b2e_handle h) {
     return 0;
 }
 
+// base_reset of the envs in `mask` (null = all) through the tcgen05 eval kernel; see reset_list_kernel
+int reset_through_pipeline(b2e_handle h, StepArgs a, void *stream) {
+    Dev &d = h->d;
+    const cudaStream_t cs = (cudaStream_t)stream;
+    a.env_list = h->reset_list; a.env_count = h->reset_count; a.loss_out = h->reset_loss;
+    a.e_begin = 0; a.e_count = d.E;
+    reset_list_kernel<<<1, 1024, 0, cs>>>(a.mask, d.E, h->reset_list, h->reset_count);
+    const int wide = d.E < 8 * h->num_sms ? d.E : 8 * h->num_sms;
+    reset_prepare_kernel<<<wide, 256, 0, cs>>>(d, a);
+    Dev dv = d;
+    dv.gnext = d.gprev;                                       // the reset gradient is the newest raw-history entry
+    if (b2e_tc2_launch(h->tc2, &dv, &a, 0, cs)) return fail(h, "tc2 launch failed (reset)");
+    reset_finish_kernel<<<wide, 256, 0, cs>>>(d, a);
+    h->launches += 4;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 int launch(b2e_handle h, StepArgs args, void *stream) {
+    if (args.mode == MODE_RESET && h->reset_pipeline) return reset_through_pipeline(h, args, stream);
     if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
     const cudaStream_t cs = (cudaStream_t)stream;
     if (h->d.generic) {
@@ -3690,7 +3831,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
     h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -3908,6 +4049,14 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         std::string err;
         h->tc2 = b2e_tc2_create(&h->d, h->num_sms, &err);
         if (!h->tc2) return bail("b2e_create: " + err);
+        // resets run through the same kernel (B2E_RESET_PIPELINE=0: the fused kernel in reset mode, kept for A/B runs)
+        if (cfg->env_kind == B2E_ENV_MULTIOPTLRS && !(getenv("B2E_RESET_PIPELINE") && atoi(getenv("B2E_RESET_PIPELINE")) == 0)) {
+            if (!dmalloc((void **)&h->reset_list, (size_t)d.E * sizeof(int)) || !dmalloc((void **)&h->reset_count, sizeof(int)) ||
+                !dmalloc((void **)&h->reset_loss, (size_t)d.E * sizeof(float)))
+                return bail("b2e_create: cudaMalloc of the reset work list failed");
+            cudaMemset(h->reset_count, 0, sizeof(int));
+            h->reset_pipeline = true;
+        }
     }
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
@@ -3922,7 +4071,7 @@ void b2e_destroy(b2e_handle h) {
     cudaFree(h->row_of_param); cudaFree(h->param_of_row); cudaFree(h->w); cudaFree(h->gprev); cudaFree(h->ringw);
     cudaFree(h->w2); cudaFree(h->g2); cudaFree(h->ws);
     b2e_tc2_destroy(h->tc2);
-    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u); cudaFree(h->part_r); cudaFree(h->slot_abs);
+    cudaFree(h->ringg); cudaFree(h->sc); cudaFree(h->gnext); cudaFree(h->part); cudaFree(h->part_u); cudaFree(h->part_r); cudaFree(h->slot_abs); cudaFree(h->reset_list); cudaFree(h->reset_count); cudaFree(h->reset_loss);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->hi) cudaStreamDestroy(h->hi);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -89,6 +89,10 @@ struct StepArgs {
     float *loss_out;
     int mode;
     int e_begin, e_count;
+    // optional work list (reset pipeline of the tcgen05 eval kernel): the envs to visit, ascending, and
+    // how many, both in device memory; null = the range e_begin .. e_begin + e_count
+    const int *env_list;
+    const int *env_count;
 };
 
 struct Stats {

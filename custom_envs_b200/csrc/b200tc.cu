@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
     float *const ts = reinterpret_cast<float *>(sm + OFF_TAIL);
     const int D = d.D, C = CC ? CC : d.C;
     const int UF = (D + 31) >> 5, TB = (D + 127) >> 7;
-    const int e_end = a.e_begin + a.e_count;
+    // work items: the envs of the range, or of the list a reset built (b200env.cu reset_list_kernel)
+    const int n_items = a.env_list ? *a.env_count : a.e_count;
+    auto env_at = [&](int i) { return a.env_list ? a.env_list[i] : a.e_begin + i; };
     // optional timeline of CTA 0 (B2E_TC_TRACE=<file>): clock64 of the n-th event of each role
     long long *const trace = (dbg[15] != 0 && blockIdx.x == 0) ? reinterpret_cast<long long *>(dbg + 16) : nullptr;
 #define TC2_TRACE(role, n) do { if (trace && lane == 0 && (n) < 512) trace[(role) * 512 + (n)] = clock64(); } while (0)
@@ -220,9 +222,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)i * 128));
         };
         uint32_t it = 0;
-        if (a.e_begin + (int)blockIdx.x < e_end && pf_units > 0) prefetch_env(a.e_begin + blockIdx.x);
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
-            if (e + (int)gridDim.x < e_end && pf_units > 0) prefetch_env(e + gridDim.x);
+        if ((int)blockIdx.x < n_items && pf_units > 0) prefetch_env(env_at(blockIdx.x));
+        for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x) {
+            const int e = env_at(it_e);
+            if (it_e + (int)gridDim.x < n_items && pf_units > 0) prefetch_env(env_at(it_e + gridDim.x));
             for (int u = 0; u < UF; ++u, ++it) {
                 const int s = it % SF;
                 mbar_wait(&bars.emptyF[s], ((it / SF) & 1) ^ 1, 1, dbg);
@@ -252,16 +255,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         uint32_t it = 0;
         // the row indices of an env sit behind two dependent global loads (cursor -> order -> row):
         // they are fetched one env ahead, so that no env starts with that latency
-        auto fetch_row = [&](int e) {
-            if (e >= e_end) return -1;
+        auto fetch_row = [&](int item) {
+            if (item >= n_items) return -1;
+            const int e = env_at(item);
             const int *idx; int cnt;
             current_batch(d, a, e, d.sc + e, idx, cnt);
             return lane < cnt ? idx[lane] : -1;
         };
-        int next_row = fetch_row(a.e_begin + blockIdx.x);
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+        int next_row = fetch_row(blockIdx.x);
+        for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x) {
             const int my_row = next_row;
-            next_row = fetch_row(e + gridDim.x);          // consumed at unit 8 / at the next env: the loads have time to land
+            next_row = fetch_row(it_e + gridDim.x);          // consumed at unit 8 / at the next env: the loads have time to land
             const char *rowp[8];
             int rbytes[8];
 #pragma unroll
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             const uint64_t ad0 = make_desc(sbase + OFF_F + F_W, 4096, 512, 1);
             const uint64_t bd0 = make_desc(sbase + OFF_F + F_X, 16, 1024, 2);
             uint32_t itF = 0, itP = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+            for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x) {
                 for (int u = 0; u < UF; ++u, ++itF) {
                     const int s = itF % SF, b = itP % NACC;
                     // The tensor core's adder truncates: a sum over all 98 K steps in ONE accumulator drifts by
@@ -343,7 +347,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             const uint64_t ahi0 = make_desc(sbase + OFF_B, 4096, 512, 1), alo0 = make_desc(sbase + OFF_B + B_XLO, 4096, 512, 1);
             uint32_t itB = 0;
             int k = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+            for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x, ++k) {
+            const int e = env_at(it_e);
                 mbar_wait(&bars.dpre_ready, k & 1, 4, dbg);
                 for (int t = 0; t < TB; ++t, ++itB) {
                     const int s = itB % SB, g = itB & 1;
@@ -383,7 +388,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         for (int i = ttid; i < N1 * CMAX; i += 128)       // the padding of the W2 rows multiplies zeros of dZ: keep it finite
             if (i % CMAX >= C) tw[N1 + i] = 0.f;
         int k = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+        for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x, ++k) {
+            const int e = env_at(it_e);
             const float *We = d.w + (size_t)e * d.Pp;
             float *gout = d.gnext + (size_t)e * d.Pp;
             const int *idx; int cnt;
@@ -562,7 +568,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         unsigned char *stg = sm + OFF_G + q * 4096;
         uint32_t itG = 0;
         int k = 0;
-        for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+        for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x, ++k) {
+            const int e = env_at(it_e);
             float gsum = 0.f;
             for (int t = 0; t < TB; ++t, ++itG) {
                 const int g = itG & 1;
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         if (warp >= 12 && warp < 12 + CONV_F_WARPS) {
             const int cid = tid - 384;                    // 0..127
             uint32_t itF = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+            for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x) {
                 for (int u = 0; u < UF; ++u, ++itF) {
                     const int s = itF % SF;
                     mbar_wait(&bars.fullF[s], (itF / SF) & 1, 14, dbg);
@@ -672,7 +679,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
             float *HT = ts + T_H;
             uint32_t itP = 0;
             int k = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x, ++k) {
+            for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x, ++k) {
+            const int e = env_at(it_e);
                 float acc[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) acc[i] = 0.f;
@@ -710,7 +718,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc2_eval_kernel(const __grid_const
         } else if (warp >= CONV_B_WARP0 && warp < CONV_B_WARP0 + CONV_B_WARPS) {
             const int cid = tid - 32 * CONV_B_WARP0;        // 0..95
             uint32_t itB = 0;
-            for (int e = a.e_begin + blockIdx.x; e < e_end; e += gridDim.x) {
+            for (int it_e = blockIdx.x; it_e < n_items; it_e += gridDim.x) {
                 for (int t = 0; t < TB; ++t, ++itB) {
                     const int s = itB % SB;
                     mbar_wait(&bars.fullB[s], (itB / SB) & 1, 13, dbg);

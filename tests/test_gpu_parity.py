@@ -809,3 +809,92 @@ def test_bench_sampled_parity_check_agrees_with_the_step(after_reset):
     bad = step_check.compare_step(ref, ref_obs, ref_rew, ref_done, seeded, device)
     assert not bad['ok']
     env.close()
+
+
+def test_reset_pipeline_of_the_tensor_core_path(monkeypatch):
+    """base_reset (envs/multioptlrs.py:66-78) on the config-4 shape runs as work list -> reshuffle + fresh
+    parameters -> tcgen05 eval -> histories + observation rows (reset_*_kernel in csrc/b200env.cu).  Against
+    the oracle's loss / gradient at the same parameters and minibatch, against b2e_eval (same kernel: bit
+    for bit), against the fused kernel in reset mode (B2E_RESET_PIPELINE=0), for a full reset, a masked
+    reset and the auto-reset inside a step; envs outside the mask are not touched."""
+    BatchedOptEnv, ProblemSpec = _mods()
+    ospec = orc.ProblemSpec('softmax', 784, (64,), 10)
+    rng = np.random.RandomState(3)
+    num_rows, num_envs = 640, 9
+    feats = rng.uniform(size=(num_rows, 784)).astype(np.float32)
+    labels = rng.randint(0, 10, num_rows).astype(np.int32)
+    targs = labels                                         # the oracle takes integer labels for softmax problems
+    perms = np.stack([orc.env_permutation(num_rows, 40 + s) for s in range(num_envs)])
+    state_names = ('params', 'grad_prev', 'adj_weights', 'adj_grads', 'adj_losses', 'raw_losses', 'raw_gsums', 'step', 'cursor')
+
+    def build():
+        return BatchedOptEnv(product_spec(ospec), feats, labels, num_envs, batch_size=32, max_batches=3,
+                             perms=perms, init_seed=21)
+
+    def snapshot(env):
+        idx, cnt = env.batch_indices()
+        return {name: env.get_state(name).cpu().numpy() for name in state_names}, idx.cpu().numpy(), cnt.cpu().numpy()
+
+    def check_reset_state(env, which, tag):
+        state, idx, cnt = snapshot(env)
+        grad, loss = env.evaluate()
+        grad, loss = grad.cpu().numpy(), loss.cpu().numpy()
+        for e in which:
+            assert np.array_equal(state['grad_prev'][e], grad[e]), (tag, e)              # the same kernel evaluated it
+            assert state['raw_losses'][e, 0] == loss[e] and not state['raw_losses'][e, 1:].any(), (tag, e)
+            assert state['step'][e] == 0 and state['cursor'][e] == 0, (tag, e)
+            assert not state['adj_losses'][e].any() and not state['adj_weights'][e].any(), (tag, e)   # read back as empty
+            mask = np.arange(32)[None, :] < cnt[e:e + 1, None]
+            ref_g, ref_l = orc.loss_and_grad(ospec, state['params'][e:e + 1], feats[idx[e:e + 1]], targs[idx[e:e + 1]], mask)
+            scale = np.abs(ref_g).mean()
+            assert abs(loss[e] - ref_l[0]) <= RTOL * abs(ref_l[0]), (tag, e)
+            assert np.abs(grad[e] - ref_g[0]).max() <= RTOL * scale, (tag, e)
+            np.testing.assert_allclose(state['raw_gsums'][e, 0], ref_g[0].sum(), rtol=0, atol=2 * RTOL * np.abs(ref_g[0]).sum())
+        return state
+
+    monkeypatch.delenv('B2E_RESET_PIPELINE', raising=False)
+    env = build()
+    obs = env.reset()
+    assert bool(torch.all(obs == -1.0))
+    first = check_reset_state(env, range(num_envs), 'full reset')
+    assert env.launch_count >= 4
+
+    # the fused kernel in reset mode starts from the same parameters and minibatches
+    monkeypatch.setenv('B2E_RESET_PIPELINE', '0')
+    old = build()
+    old.reset()
+    old_state, old_idx, old_cnt = snapshot(old)
+    monkeypatch.delenv('B2E_RESET_PIPELINE')
+    assert np.array_equal(old_state['params'], first['params']) and np.array_equal(old_idx, snapshot(env)[1])
+    scale = np.abs(first['grad_prev']).mean(axis=1, keepdims=True)
+    # two fp32 evaluations, each within RTOL of the exact gradient: they are within 2 RTOL of each other
+    assert (np.abs(old_state['grad_prev'] - first['grad_prev']) / scale).max() <= 2 * RTOL
+    np.testing.assert_allclose(old_state['raw_losses'], first['raw_losses'], rtol=RTOL)
+    old.close()
+
+    # two steps, then a masked reset with given parameters: the other envs keep every bit of their state
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    for _ in range(2):
+        env.step(torch.rand(env.num_rows, device='cuda', generator=gen) * 2)
+    before, idx_before, _ = snapshot(env)
+    obs_before = env.obs.clone()
+    mask = np.zeros(num_envs, bool)
+    mask[[0, 4, 8]] = True
+    init = np.stack([orc.glorot_uniform_init(ospec, rng) for _ in range(num_envs)])
+    obs = env.reset(env_mask=mask, init_params=init).reshape(num_envs, -1)
+    assert bool(torch.all(obs[torch.as_tensor(mask)] == -1.0))
+    assert torch.equal(obs[torch.as_tensor(~mask)], obs_before.reshape(num_envs, -1)[torch.as_tensor(~mask)])
+    after = check_reset_state(env, np.flatnonzero(mask), 'masked reset')
+    assert np.array_equal(after['params'][mask], init[mask])
+    for name in state_names:
+        assert np.array_equal(after[name][~mask], before[name][~mask]), name
+    assert np.array_equal(snapshot(env)[1][~mask], idx_before[~mask])
+
+    # auto-reset inside a step: envs 1,2,3,5,6,7 are at step 2 of 3 -> done now; 0,4,8 were just reset
+    _, _, done, _ = env.step(torch.rand(env.num_rows, device='cuda', generator=gen) * 2)
+    done = done.cpu().numpy().astype(bool)
+    assert np.array_equal(done, ~mask)
+    assert bool(torch.all(env.obs.reshape(num_envs, -1)[torch.as_tensor(done)] == -1.0))
+    final = check_reset_state(env, np.flatnonzero(done), 'auto-reset')
+    assert np.all(final['step'][mask] == 1)
+    env.close()
