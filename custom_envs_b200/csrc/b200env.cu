@@ -29,6 +29,7 @@
 #include "b200env_shared.cuh"
 #include "b200tc.h"
 #include "b200env_internal.h"
+#include "b200tiny.h"
 
 namespace {
 
@@ -3412,6 +3413,7 @@ struct b2e_env {
     int *reset_list, *reset_count;   // reset pipeline of the tcgen05 path: work list, its length, losses of the reset evals
     float *reset_loss;
     bool reset_pipeline;
+    bool use_tiny;                   // warp-per-env kernel for tiny problems (b200tiny.cu; B2E_TINY=0 disables)
     double *part_r, *slot_abs;       // ring-only steps: ring_adjg_kernel's partial sums, per-slot sums of |adjusted x|
     cudaStream_t side;               // the observation kernel runs here (lowest priority) ...
     cudaStream_t hi;                 // ... next to the compute kernel (highest priority)
@@ -3746,6 +3748,12 @@ int reset_through_pipeline(b2e_handle h, StepArgs a, void *stream) {
 
 int launch(b2e_handle h, StepArgs args, void *stream) {
     if (args.mode == MODE_RESET && h->reset_pipeline) return reset_through_pipeline(h, args, stream);
+    if (h->use_tiny && (args.mode == MODE_STEP || args.mode == MODE_RESET)) {
+        if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
+        h->launches++;
+        if (b2e_tiny_launch(&h->d, &args, stream)) return fail(h, "tiny kernel launch failed");
+        return 0;
+    }
     if (args.e_count == 0) { args.e_begin = 0; args.e_count = h->d.E; }
     const cudaStream_t cs = (cudaStream_t)stream;
     if (h->d.generic) {
@@ -3831,7 +3839,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
     h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false; h->use_tiny = false;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -4058,6 +4066,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
             h->reset_pipeline = true;
         }
     }
+    h->use_tiny = b2e_tiny_supported(&h->d) && !(getenv("B2E_TINY") && atoi(getenv("B2E_TINY")) == 0);
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
