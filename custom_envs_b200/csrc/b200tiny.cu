@@ -40,13 +40,20 @@ struct Batch {
 __device__ __forceinline__ float ratio_nn(float num, float den) { return nan_to_num_f(num / fabsf(den)); }
 __device__ __forceinline__ float clip_only_m1(float x) { return fminf(fmaxf(x, -100.0f), 100.0f) - 1.0f; }
 
+// DD / CC > 0: feature and output counts known at compile time (iris: 4, 3), which keeps the unrolled code -- every
+// warp runs it exactly once, so the kernel is bound by instruction fetch -- as short as the problem
+template <int DD, int CC>
 __device__ __forceinline__ void load_batch(const Dev &d, const StepArgs &a, int e, const EnvScalars *sc, int lane, Batch &b) {
+    constexpr int DB = DD ? DD : DMAX, CB = CC ? CC : CMAX;
+    const int D = DD ? DD : d.D, C = CC ? CC : d.C;
     const int *idx;
     current_batch(d, a, e, sc, idx, b.cnt);
     const bool live = lane < b.cnt;
     const size_t row = live ? (size_t)idx[lane] : 0;
 #pragma unroll
-    for (int k = 0; k < DMAX; ++k) b.x[k] = (live && k < d.D) ? d.X[row * d.Dp + k] : 0.f;
+    for (int k = 0; k < DMAX; ++k) b.x[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DB; ++k) b.x[k] = (live && k < D) ? d.X[row * d.Dp + k] : 0.f;
     b.y = 0;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) b.yt[c] = 0.f;
@@ -54,14 +61,16 @@ __device__ __forceinline__ void load_batch(const Dev &d, const StepArgs &a, int 
         b.y = live ? d.labels[row] : 0;
     } else {
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) if (live && c < d.C) b.yt[c] = d.targets[row * d.C + c];
+        for (int c = 0; c < CB; ++c) if (live && c < C) b.yt[c] = d.targets[row * C + c];
     }
 }
 
 // loss (mean over the minibatch) and batch-SUM gradient (problems/optimize_nn.py:47-52) at the parameters in S.w;
 // g[j] = component lane + 32 j
+template <int DD, int CC>
 __device__ __forceinline__ float eval(const Dev &d, WarpSmem &S, const Batch &b, int lane, float (&g)[PL]) {
-    const int D = d.D, C = d.C, P1 = d.P1;
+    constexpr int DMAX = DD ? DD : tiny::DMAX, CMAX = CC ? CC : tiny::CMAX;      // loop bounds of this instantiation
+    const int D = DD ? DD : d.D, C = CC ? CC : d.C, P1 = d.P1;
     float z[CMAX];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
@@ -98,9 +107,9 @@ __device__ __forceinline__ float eval(const Dev &d, WarpSmem &S, const Batch &b,
     // mean loss: the samples in index order, as the fused kernel adds them
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < DMAX; ++k) S.xs[lane * DMAX + k] = b.x[k];
+    for (int k = 0; k < DMAX; ++k) S.xs[lane * tiny::DMAX + k] = b.x[k];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) S.zs[lane * CMAX + c] = z[c];
+    for (int c = 0; c < CMAX; ++c) S.zs[lane * tiny::CMAX + c] = z[c];
     float lsum = 0.f;
     for (int s = 0; s < b.cnt; ++s) lsum += __shfl_sync(0xffffffffu, loss, s);
     __syncwarp();
@@ -110,10 +119,10 @@ __device__ __forceinline__ float eval(const Dev &d, WarpSmem &S, const Batch &b,
         float acc = 0.f;
         if (p < P1) {
             const int k = p / C, c = p - k * C;
-            for (int s = 0; s < b.cnt; ++s) acc = fmaf(S.xs[s * DMAX + k], S.zs[s * CMAX + c], acc);
+            for (int s = 0; s < b.cnt; ++s) acc = fmaf(S.xs[s * tiny::DMAX + k], S.zs[s * tiny::CMAX + c], acc);
         } else if (p < d.P) {
             const int c = p - P1;
-            for (int s = 0; s < b.cnt; ++s) acc += S.zs[s * CMAX + c];
+            for (int s = 0; s < b.cnt; ++s) acc += S.zs[s * tiny::CMAX + c];
         }
         g[j] = acc;
     }
@@ -133,7 +142,8 @@ __device__ __forceinline__ void warp_shuffle_order(const Dev &d, int e, EnvScala
 }
 
 // base_reset (multioptlrs.py:66-78) of one env by its warp
-__device__ void reset_one(const Dev &d, const StepArgs &a, WarpSmem &S, int e, int lane) {
+template <int DD, int CC>
+__device__ __noinline__ void reset_one(const Dev &d, const StepArgs &a, WarpSmem &S, int e, int lane) {
     EnvScalars *sc = d.sc + e;
     if (d.index_mode == B2E_INDEX_INTERNAL) {
         warp_shuffle_order(d, e, sc, lane);                   // optimize_nn.py:114-120
@@ -141,7 +151,7 @@ __device__ void reset_one(const Dev &d, const StepArgs &a, WarpSmem &S, int e, i
         __syncwarp();
     }
     Batch b;
-    load_batch(d, a, e, sc, lane, b);
+    load_batch<DD, CC>(d, a, e, sc, lane, b);
     const int episode = sc->episode;
     float *wE = d.w + (size_t)e * d.Pp;
 #pragma unroll
@@ -157,7 +167,7 @@ __device__ void reset_one(const Dev &d, const StepArgs &a, WarpSmem &S, int e, i
     }
     __syncwarp();
     float g[PL];
-    const float loss = eval(d, S, b, lane, g);
+    const float loss = eval<DD, CC>(d, S, b, lane, g);
     float gs = 0.f;
     float *gE = d.gprev + (size_t)e * d.Pp;
 #pragma unroll
@@ -185,7 +195,7 @@ __device__ void reset_one(const Dev &d, const StepArgs &a, WarpSmem &S, int e, i
     __syncwarp();
 }
 
-template <int HT>
+template <int HT, int DD, int CC>
 __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_constant__ Dev d, const __grid_constant__ StepArgs a) {
     __shared__ WarpSmem smem[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,16 +203,17 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
     if (e >= a.e_begin + a.e_count) return;
     WarpSmem &S = smem[warp];
     if (a.mode == MODE_RESET) {
-        if (a.mask == nullptr || a.mask[e]) reset_one(d, a, S, e, lane);
+        if (a.mask == nullptr || a.mask[e]) reset_one<DD, CC>(d, a, S, e, lane);
         return;
     }
     const int H = HT ? HT : d.H, P = d.P, OD = 3 * H;
     EnvScalars *sc = d.sc + e;
+    constexpr int HB = HT ? HT : B2E_MAX_HISTORY;
     Batch b;
-    load_batch(d, a, e, sc, lane, b);
+    load_batch<DD, CC>(d, a, e, sc, lane, b);
     float *wE = d.w + (size_t)e * d.Pp;
     float *gE = d.gprev + (size_t)e * d.Pp;
-    float wv[PL], g0[PL], gt[PL];
+    float wv[PL], gt[PL];
 #pragma unroll
     for (int j = 0; j < PL; ++j) {
         const int p = lane + 32 * j;
@@ -210,7 +221,6 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
         S.w[p] = wv[j];
     }
     __syncwarp();
-    eval(d, S, b, lane, g0);                                  // multioptlrs.py:85
     const int head_new = (sc->head + 1) % H;
     const int nvalid_new = min(sc->nvalid + 1, H);
     float *rw = d.ringw + (size_t)e * H * d.Pp, *rg = d.ringg + (size_t)e * H * d.Pp;
@@ -218,31 +228,37 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
     double s_lr = 0.0, s_lr2 = 0.0;
     float aw[PL];
     int row[PL];
-    __syncwarp();
+    float loss = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {                     // one copy of the eval code serves both evaluations
+        loss = eval<DD, CC>(d, S, b, lane, gt);                // multioptlrs.py:85 at w_{t-1}, :88 at w_t (same minibatch)
+        if (pass == 0) {
+            __syncwarp();
 #pragma unroll
-    for (int j = 0; j < PL; ++j) {                             // multioptlrs.py:86-87, utils_env.py:158-159
-        const int p = lane + 32 * j;
-        row[j] = 0; aw[j] = 0.f;
-        if (p < P) {
-            row[j] = d.row_lex ? d.row_of_param[p] : p;
-            const float lr = action_to_lr(a.actions[(size_t)e * P + row[j]], d.act_ver);
-            const float wn = fmaf(-g0[j], lr, wv[j]);
-            aw[j] = ratio_nn(wn, wv[j]);
-            s_absw += fabsf(wn);
-            s_lr += (double)lr;
-            s_lr2 += (double)lr * (double)lr;
-            wE[p] = wn;
-            rw[(size_t)head_new * d.Pp + p] = aw[j];
-            S.w[p] = wn;
+            for (int j = 0; j < PL; ++j) {                     // multioptlrs.py:86-87, utils_env.py:158-159
+                const int p = lane + 32 * j;
+                row[j] = 0; aw[j] = 0.f;
+                if (p < P) {
+                    row[j] = d.row_lex ? d.row_of_param[p] : p;
+                    const float lr = action_to_lr(a.actions[(size_t)e * P + row[j]], d.act_ver);
+                    const float wn = fmaf(-gt[j], lr, wv[j]);
+                    aw[j] = ratio_nn(wn, wv[j]);
+                    s_absw += fabsf(wn);
+                    s_lr += (double)lr;
+                    s_lr2 += (double)lr * (double)lr;
+                    wE[p] = wn;
+                    rw[(size_t)head_new * d.Pp + p] = aw[j];
+                    S.w[p] = wn;
+                }
+            }
+            __syncwarp();
         }
     }
-    __syncwarp();
-    const float loss = eval(d, S, b, lane, gt);               // multioptlrs.py:88: same minibatch, w_t
     const double adjl = nan_to_num_d((double)loss / fabs((double)sc->loss_prev));
-    float ol[B2E_MAX_HISTORY];
+    float ol[HB];
     double labs = 0.0;
 #pragma unroll
-    for (int h = 0; h < B2E_MAX_HISTORY; ++h) {
+    for (int h = 0; h < HB; ++h) {
         if (h < H) {
             float v = 0.f;
             if (h == 0) v = (float)adjl;
@@ -268,7 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
             rg[(size_t)head_new * d.Pp + p] = ag;
             float *orow = S.obs + row[j] * OD;
 #pragma unroll
-            for (int h = 0; h < B2E_MAX_HISTORY; ++h) {
+            for (int h = 0; h < HB; ++h) {
                 if (h < H) {
                     float w_h = 0.f, g_h = 0.f;
                     if (h == 0) { w_h = aw[j]; g_h = ag; }
@@ -324,26 +340,26 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
         sc->step = step;
         double gsum = 0.0, lsum = 0.0;
         for (int i = 0; i < RAW_DEPTH; ++i) { gsum += sc->raw_gsum[i]; lsum += (double)sc->raw_loss[i]; }
-        const double Pd = (double)P;
-        const double lr_mean = t_lr / Pd;
-        double lr_var = t_lr2 / Pd - lr_mean * lr_mean;
+        const double Pd = (double)P, invP = 1.0 / Pd;        // one fp64 division instead of eight
+        const double lr_mean = t_lr * invP;
+        double lr_var = t_lr2 * invP - lr_mean * lr_mean;
         lr_var = lr_var > 0.0 ? lr_var : 0.0;
         const double ssum = t_state + Pd * labs;
         double *info = a.info + (size_t)e * B2E_INFO_STRIDE;
         info[0] = done ? (double)loss : nan("");
         info[1] = (double)loss;
-        info[2] = t_absw / Pd;
+        info[2] = t_absw * invP;
         info[3] = t_absw;
         info[4] = lr_mean;
         info[5] = sqrt(lr_var);
-        info[6] = ssum / (Pd * (double)OD);
+        info[6] = ssum * invP / (double)OD;
         info[7] = ssum;
-        info[8] = gsum / (RAW_DEPTH * Pd);
+        info[8] = gsum * invP * (1.0 / RAW_DEPTH);
         info[9] = gsum;
-        info[10] = lsum / RAW_DEPTH;
+        info[10] = lsum * (1.0 / RAW_DEPTH);
         info[11] = adjl;
-        info[12] = t_absadjg / Pd;
-        info[13] = t_gdiff / Pd;
+        info[12] = t_absadjg * invP;
+        info[13] = t_gdiff * invP;
         info[14] = reward;
         info[15] = (double)step;
         a.reward[e] = (float)reward;
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32) tiny_env_kernel(const __grid_const
     flags = __shfl_sync(0xffffffffu, flags, 0);
     __syncwarp();
     if (flags & 2) warp_shuffle_order(d, e, sc, lane);
-    if ((flags & 1) && d.auto_reset) reset_one(d, a, S, e, lane);
+    if ((flags & 1) && d.auto_reset) reset_one<DD, CC>(d, a, S, e, lane);
 }
 
 }  // namespace tiny
@@ -376,7 +392,9 @@ int b2e_tiny_launch(const void *dev, const void *args, void *stream) {
     const Dev &d = *static_cast<const Dev *>(dev);
     const StepArgs &a = *static_cast<const StepArgs *>(args);
     const int grid = (a.e_count + tiny::WARPS - 1) / tiny::WARPS;
-    if (d.H == 5) tiny::tiny_env_kernel<5><<<grid, tiny::WARPS * 32, 0, (cudaStream_t)stream>>>(d, a);
-    else tiny::tiny_env_kernel<0><<<grid, tiny::WARPS * 32, 0, (cudaStream_t)stream>>>(d, a);
+    const cudaStream_t cs = (cudaStream_t)stream;
+    if (d.H == 5 && d.D == 4 && d.C == 3) tiny::tiny_env_kernel<5, 4, 3><<<grid, tiny::WARPS * 32, 0, cs>>>(d, a);   // iris
+    else if (d.H == 5) tiny::tiny_env_kernel<5, 0, 0><<<grid, tiny::WARPS * 32, 0, cs>>>(d, a);
+    else tiny::tiny_env_kernel<0, 0, 0><<<grid, tiny::WARPS * 32, 0, cs>>>(d, a);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
