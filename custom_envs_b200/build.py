@@ -6,11 +6,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SOURCES = [os.path.join(_HERE, 'csrc', 'b200env.cu'), os.path.join(_HERE, 'csrc', 'b200tc.cu'),
            os.path.join(_HERE, 'csrc', 'b200data.cu'), os.path.join(_HERE, 'csrc', 'b200policy.cu'),
-           os.path.join(_HERE, 'csrc', 'b200tiny.cu')]
+           os.path.join(_HERE, 'csrc', 'b200tiny.cu'), os.path.join(_HERE, 'csrc', 'b200thin.cu')]
 HEADERS = [os.path.join(ROOT, 'include', 'b200env.h'), os.path.join(ROOT, 'include', 'b200data.h'),
            os.path.join(ROOT, 'include', 'b200policy.h'),
            os.path.join(_HERE, 'csrc', 'b200env_shared.cuh'), os.path.join(_HERE, 'csrc', 'b200tc.h'),
-           os.path.join(_HERE, 'csrc', 'b200env_internal.h'), os.path.join(_HERE, 'csrc', 'b200tiny.h')]
+           os.path.join(_HERE, 'csrc', 'b200env_internal.h'), os.path.join(_HERE, 'csrc', 'b200tiny.h'), os.path.join(_HERE, 'csrc', 'b200thin.h')]
 OBJ_DIR = os.path.join(_HERE, 'csrc', '_obj')
 OUTPUT = os.path.join(_HERE, 'libb200env.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

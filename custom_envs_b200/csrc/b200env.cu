@@ -30,6 +30,7 @@
 #include "b200tc.h"
 #include "b200env_internal.h"
 #include "b200tiny.h"
+#include "b200thin.h"
 
 namespace {
 
@@ -3394,6 +3395,7 @@ struct b2e_env {
     bool eval_bulk;                  // ... and its bulk-copy / mbarrier pipelined form (B2E_EVAL_BULK=0 disables)
     int nchunks, eval_ctas_per_sm;   // B2E_CHUNKS experiment
     bool use_thin;                   // softmax regression: thin_eval_kernel
+    bool use_thin2;                  // ... its shared-memory-resident successor for 10 classes (b200thin.cu; B2E_THIN2=0 disables)
     size_t smem_thin;
     int thin_kc;
     bool use_tc;                     // tcgen05 eval kernel replaces eval_kernel
@@ -3839,7 +3841,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
     h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false; h->use_tiny = false;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false; h->use_tiny = false; h->use_thin2 = false;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -4067,6 +4069,8 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
         }
     }
     h->use_tiny = b2e_tiny_supported(&h->d) && !(getenv("B2E_TINY") && atoi(getenv("B2E_TINY")) == 0);
+    h->use_thin2 = h->use_thin && b2e_thin2_supported(&h->d) && !(getenv("B2E_THIN2") && atoi(getenv("B2E_THIN2")) == 0) &&
+                   b2e_thin2_prepare(&h->d) == 0;
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
@@ -4191,7 +4195,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
             CUDA_TRY(h, cudaGetLastError());
         } else if (h->use_thin) {
             const int grid_ev = d.E < h->eval_grid ? d.E : h->eval_grid;
-            { Dev dt = d; dt.KT = h->thin_kc;
+            if (h->use_thin2) { if (b2e_thin2_launch(&d, &a, 1, h->num_sms, main_s)) return fail(h, "thin2 launch failed"); }
+            else { Dev dt = d; dt.KT = h->thin_kc;
           if (d.C == 10) thin_eval_kernel<true, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
           else thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
             h->launches++;
@@ -4268,7 +4273,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         else if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        { Dev dt = d; dt.KT = h->thin_kc;
+        if (h->use_thin2) { if (b2e_thin2_launch(&d, &a, 0, h->num_sms, main_s)) return fail(h, "thin2 launch failed"); }
+        else { Dev dt = d; dt.KT = h->thin_kc;
           if (d.C == 10) thin_eval_kernel<false, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
           else thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {                                                 // generic dense stack
@@ -4290,7 +4296,8 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         else if (h->eval_c) eval_kernel<true, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<true><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        { Dev dt = d; dt.KT = h->thin_kc;
+        if (h->use_thin2) { if (b2e_thin2_launch(&d, &a, 1, h->num_sms, main_s)) return fail(h, "thin2 launch failed"); }
+        else { Dev dt = d; dt.KT = h->thin_kc;
           if (d.C == 10) thin_eval_kernel<true, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
           else thin_eval_kernel<true><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
     } else {

@@ -951,3 +951,47 @@ def test_warp_per_env_kernel_equals_the_block_per_env_kernel(name, depth, monkey
         resets += int(new[2].sum())
     # two episode ends per env; the squared loss of the linear regression also exceeds 1e4 under lr = 100
     assert resets >= 2 * num_envs + (1 if name == 'linreg' else 0)
+
+
+def test_resident_minibatch_eval_kernel_against_the_chunked_one(monkeypatch):
+    """BASELINE config 3 (softmax regression 784 -> 10): `thin2_eval_kernel` (csrc/b200thin.cu, the minibatch
+    resident in shared memory) against `thin_eval_kernel` (B2E_THIN2=0, feature chunks streamed twice) over two
+    episodes with a ragged last minibatch.  Two fp32 evaluations of the same sums in different orders: gradients
+    within 2 RTOL of the gradient scale, losses / rewards within RTOL, done flags and index streams equal."""
+    BatchedOptEnv, _ = _mods()
+    spec, num_rows, batch, _ = SPECS['softmax_784x10']
+    num_rows, num_envs = 304, 11                               # 304 = 9 * 32 + 16: a half-full last minibatch
+    feats, targs = make_data(spec, num_rows)
+    perms = np.stack([orc.env_permutation(num_rows, 80 + s) for s in range(num_envs)])
+    runs = []
+    for resident in (True, False):
+        if resident:
+            monkeypatch.delenv('B2E_THIN2', raising=False)
+        else:
+            monkeypatch.setenv('B2E_THIN2', '0')
+        env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=batch, max_batches=12,
+                            perms=perms, init_seed=17)
+        env.reset()
+        gen = torch.Generator(device='cuda').manual_seed(8)
+        rec = []
+        for t in range(25):
+            actions = torch.rand(env.num_rows, device='cuda', generator=gen) * 2.0
+            obs, rew, done, info = env.step(actions)
+            rec.append((rew.cpu().numpy().copy(), done.cpu().numpy().copy(), env.get_state('grad_prev').cpu().numpy(),
+                        env.get_state('params').cpu().numpy(), env.get_state('raw_losses').cpu().numpy(),
+                        env.batch_indices()[0].cpu().numpy(), env.batch_indices()[1].cpu().numpy()))
+            # identical states for the next step: the runs are compared step by step, not as diverging trajectories
+            if not resident:
+                env.set_state('params', runs[0][t][3])
+                env.set_state('grad_prev', runs[0][t][2])
+        runs.append(rec)
+        env.close()
+    ragged = 0
+    for t, (new, old) in enumerate(zip(*runs)):
+        assert np.array_equal(new[1], old[1]) and np.array_equal(new[5], old[5]) and np.array_equal(new[6], old[6]), t
+        ragged += int((new[6] < batch).sum())
+        scale = np.abs(old[2]).mean(axis=1, keepdims=True) + 1e-30
+        assert (np.abs(new[2] - old[2]) / scale).max() <= 2 * RTOL, (t, float((np.abs(new[2] - old[2]) / scale).max()))
+        np.testing.assert_allclose(new[4][:, 0], old[4][:, 0], rtol=RTOL, err_msg=str(t))
+        np.testing.assert_allclose(new[0], old[0], rtol=20 * RTOL, atol=20 * RTOL, err_msg=str(t))
+    assert ragged >= 2 * num_envs
