@@ -376,6 +376,38 @@ def gpu_arm(args):
     for i in range(3):                                  # back to a steady state with valid history rings
         env.step(actions[i & 1])
 
+    # ---- policy in the loop on the device: the library's tcgen05 policy kernel reading the env's rings,
+    # ring-only env steps; nothing but the action vector and E rewards / flags / info rows exists per step
+    policy_loop = None
+    if not args.skip_policy_loop:
+        try:
+            from custom_envs_b200.vectorize.device_policy import DevicePolicy, device_policy_rollout
+            from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy
+            torch.manual_seed(5 + rank)
+            net = SharedMlpPolicy(env.obs_dim).to(device)
+            dev_policy = DevicePolicy.from_torch(net)                   # noise std = exp(log_std) of the network
+            device_policy_rollout(env, dev_policy, 3, ring_only=True)
+            pl_steps = 10
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            ev0.record()
+            device_policy_rollout(env, dev_policy, pl_steps, ring_only=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            pl_ms = ev0.elapsed_time(ev1) / pl_steps
+            if world > 1:
+                t = torch.tensor([pl_ms], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                pl_ms = float(t.item())
+            policy_loop = {'value': envs_all / (pl_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': pl_ms, 'steps': pl_steps,
+                           'what': 'closed loop on the device: b2p_act_env (MlpPolicy 15-64-64-1 tanh, bf16 tcgen05, reads the '
+                                   'adjusted-history rings) -> b2e_step(obs_out = NULL); %d agent rows per step and GPU'
+                                   % env.num_rows}
+            dev_policy.close()
+            env.step(actions[0])                                         # a dense step: observation rows are current again
+        except Exception as exc:                                        # noqa: BLE001  (auxiliary figure: never lose the line over it)
+            policy_loop = {'error': '%s: %s' % (type(exc).__name__, exc)}
+
     # ---- end to end through the reference-facing VecEnv call with host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     vec = DeviceOptVecEnv(env)
@@ -483,6 +515,7 @@ def gpu_arm(args):
                                               'ms': dominant['ms']} if dominant else None),
                          'kernels': [dict(k, frac=k['gbs'] / peak) for k in kernels]},
             'parity': parity,
+            'policy_loop': policy_loop,
             'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
                              'threads': threads, 'envs_per_thread': 8, 'rows': CPU_ROWS,
                              'sample': '%d envs x %d steps of the workload (oracle vectorised numpy float32, '
@@ -507,6 +540,7 @@ def main():
     parser.add_argument('--e2e-steps', type=int, default=5)
     parser.add_argument('--envs-total', type=int, default=0,
                         help='strong scaling: this many envs sharded over all ranks (overrides --envs)')
+    parser.add_argument('--skip-policy-loop', action='store_true', help='skip the device policy-in-the-loop figure')
     parser.add_argument('--skip-faithful', action='store_true', help='skip the ~25 s per-env-object CPU baseline')
     args = parser.parse_args()
     if args.impl == 'reference':

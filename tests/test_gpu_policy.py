@@ -189,3 +189,35 @@ def test_policy_rollout_on_the_rings_equals_rollout_on_observation_rows():
         env.close()
     assert results[0][1] == results[1][1] == 4
     assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][2], results[1][2])
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_env_and_policy_on_a_device_that_is_not_current():
+    """Every entry point runs on the handle's own device whatever the caller's current device is: an env
+    batch and a policy built with device='cuda:1' while cuda:0 is current give the trajectories of the same objects
+    on cuda:0, bit for bit."""
+    results = []
+    for dev in ('cuda:0', 'cuda:1'):
+        torch.cuda.set_device(0)
+        rng = np.random.RandomState(0)
+        feats = rng.uniform(size=(320, 784)).astype(np.float32)
+        labels = rng.randint(0, 10, 320).astype(np.int32)
+        env = BatchedOptEnv(ProblemSpec('softmax', 784, (64,), 10), feats, labels, 3, batch_size=32, max_batches=5,
+                            perms=env_permutations(320, [0, 1, 2]), init_seed=9, device=dev)
+        assert torch.cuda.current_device() == 0
+        env.reset()
+        policy = make_policy(15, seed=4, scale=1.5).to(dev)
+        dpol = DevicePolicy.from_torch(policy.pi)
+        assert dpol.device == torch.device(dev) and env.obs.device == torch.device(dev)
+        outs = []
+        for t in range(7):
+            actions = dpol.act_env(env) if t % 2 else dpol.act(env.obs)
+            obs, rew, done, info = env.step(actions)
+            outs.append((obs.cpu(), rew.cpu(), done.cpu(), info.cpu(), actions.cpu()))
+        assert torch.cuda.current_device() == 0
+        results.append(outs)
+        dpol.close()
+        env.close()
+    for a, b in zip(*results):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
