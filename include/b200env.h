@@ -121,7 +121,10 @@ int b2e_reset(b2e_handle h, const uint8_t *env_mask, const float *init_params,
 /* OptVecEnv.step_async + step_wait (vectorize/optvecenv.py:70-88) = E x
  * MultiOptLRs.base_step / MultiOptimize.base_step.
  *   actions   float32 [E*P]  one action per agent row, VecEnv row order
- *   obs_out   float32 [E*P, obs_dim]
+ *   obs_out   float32 [E*P, obs_dim], or NULL for a RING-ONLY step (MultiOptLRs envs on the large-problem
+ *             pipeline): the observation rows are not materialised -- the adjusted-history rings, which a
+ *             device policy reads in place (b200policy.h, b2p_act_env), are the observation; state, rewards,
+ *             done flags and info are those of the ordinary step
  *   reward_out float32 [E], done_out uint8 [E]   (per env; the VecEnv surface repeats them P times)
  *   info_out  double  [E, B2E_INFO_STRIDE]: the 14 values of envs/multioptlrs.py:111-127 in
  *             that order (loss = NaN unless terminal), then episode r, episode l
