@@ -12,15 +12,15 @@
 //   D2 [128 x 64] = A2 . [W2 | b2 | 0]^T     five MMAs
 //   mean = tanh(D2) . w3 + b3                 FFMA on the fp32 accumulators, lane = row
 //
-// Persistent, one 512-thread CTA per SM, FOUR independent groups of four warps; every group runs its own
+// Persistent, one 768-thread CTA per SM, SIX independent groups of four warps; every group runs its own
 // tiles start to finish (operand staging, MMA issue by its thread 0, tcgen05.commit -> the group's
 // mbarrier, tcgen05.ld epilogues), so while one group waits for its MMA the SM's MUFU units -- the
-// bound of this kernel: 128 tanh per row, 16 per clock per SM -- are busy with the other three.
-// TMEM: 512 columns = 4 groups x (D1 | D2).  Operands use the no-swizzle K-major canonical layout: core
+// bound of this kernel: 128 tanh per row, 16 per clock per SM -- are busy with the other five (four groups
+// reach 0.63 of that rate, six 0.75).  TMEM: 64 columns per group, D2 overwrites D1 (read out before).  Operands use the no-swizzle K-major canonical layout: core
 // matrices of 8 rows x 16 bytes, contiguous (128 B), LBO = 128 (next core matrix along K), SBO = K/8 * 128
 // (next 8 rows).
 //
-// Two front ends: dense rows (what b2e_step wrote; one 7.5 KB bulk copy per tile, double buffered) and
+// Two front ends: dense rows (what b2e_step wrote; one 7.5 KB bulk copy per tile, requested a tile ahead) and
 // the env's adjusted-history rings (MultiOptLRs; lane = parameter, 2H coalesced 4-byte loads prefetched one
 // tile ahead; the 3H observation words per agent never exist in HBM).
 #include <cuda_runtime.h>
@@ -37,17 +37,21 @@
 namespace {
 namespace pol {
 
-constexpr int TILE = 128, HID = B2P_HIDDEN, K1 = 16, K2 = 80, GROUPS = 4, THREADS = GROUPS * 128;
+#ifndef B2P_GROUPS
+#define B2P_GROUPS 6
+#endif
+constexpr int TILE = 128, HID = B2P_HIDDEN, K1 = 16, K2 = 80, GROUPS = B2P_GROUPS, THREADS = GROUPS * 128;
+constexpr int NSTG = GROUPS <= 4 ? 2 : 1;        // staging buffers of the dense front end per group (shared memory budget)
 constexpr int XMAX = B2P_MAX_OBS_DIM;
 constexpr int SBO1 = (K1 / 8) * 128, SBO2 = (K2 / 8) * 128;
 constexpr int A1_BYTES = (TILE / 8) * SBO1, A2_BYTES = (TILE / 8) * SBO2;
 constexpr int STAGE_BYTES = TILE * XMAX * 4;
-constexpr int G_BYTES = 2 * STAGE_BYTES + A1_BYTES + A2_BYTES;
+constexpr int G_BYTES = NSTG * STAGE_BYTES + A1_BYTES + A2_BYTES;
 constexpr int OFF_B1 = GROUPS * G_BYTES, B1_BYTES = (HID / 8) * SBO1;
 constexpr int OFF_B2 = OFF_B1 + B1_BYTES, B2_BYTES = (HID / 8) * SBO2;
 constexpr int OFF_W3 = OFF_B2 + B2_BYTES;
 constexpr int SMEM_BYTES = OFF_W3 + (HID + 4) * 4 + 128;   // + slack to align the base to 128 bytes
-constexpr int TMEM_COLS = 512;
+constexpr int TMEM_COLS = GROUPS <= 4 ? 256 : 512;    // 64 columns per group: D2 overwrites D1, which is fully read before the second layer's MMAs are issued
 static_assert(G_BYTES % 128 == 0 && OFF_B1 % 128 == 0 && OFF_B2 % 128 == 0, "operand blocks are 128-byte aligned");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 
@@ -101,6 +105,12 @@ __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 12
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
                  : "r"(taddr))
 
+#define B2P_LD16(taddr, v) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(taddr))
+
 __device__ __forceinline__ float tanh_f32(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
     const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
     unsigned char *const sm = smem_raw + (sbase - smem_u32(smem_raw));
     unsigned char *const gsm = sm + g * G_BYTES;
-    unsigned char *const A1 = gsm + 2 * STAGE_BYTES, *const A2 = A1 + A1_BYTES;
+    unsigned char *const A1 = gsm + NSTG * STAGE_BYTES, *const A2 = A1 + A1_BYTES;
     float *const w3s = reinterpret_cast<float *>(sm + OFF_W3);
     const int od = a.obs_dim;
 
@@ -180,10 +190,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);   // f32 += bf16 . bf16, both K-major
-    const uint64_t a1d = make_desc(sbase + g * G_BYTES + 2 * STAGE_BYTES, 128, SBO1);
-    const uint64_t a2d = make_desc(sbase + g * G_BYTES + 2 * STAGE_BYTES + A1_BYTES, 128, SBO2);
+    const uint64_t a1d = make_desc(sbase + g * G_BYTES + NSTG * STAGE_BYTES, 128, SBO1);
+    const uint64_t a2d = make_desc(sbase + g * G_BYTES + NSTG * STAGE_BYTES + A1_BYTES, 128, SBO2);
     const uint64_t b1d = make_desc(sbase + OFF_B1, 128, SBO1), b2d = make_desc(sbase + OFF_B2, 128, SBO2);
-    const uint32_t tm1 = tmem + 128 * g, tm2 = tm1 + 64;
+    const uint32_t tm1 = tmem + 64 * g, tm2 = tm1;
     const uint32_t tlane = (uint32_t)(wq * 32) << 16;
     const float b3 = w3s[HID];
 
@@ -303,9 +313,9 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
         if (RING) {
             ring_row(nxt, x);
         } else {
-            const int b = n & 1;
-            if (c.valid) fetch_dense(c.tile, b ^ 1);
-            mbar_wait(&obs_full[g][b], (uint32_t)(n >> 1) & 1u);
+            const int b = n % NSTG;
+            if (NSTG == 2 && c.valid) fetch_dense(c.tile, b ^ 1);
+            mbar_wait(&obs_full[g][b], (uint32_t)(n / NSTG) & 1u);
             const float *st = reinterpret_cast<const float *>(gsm + b * STAGE_BYTES) + gt * od;
             const bool live = tile * TILE + gt < a.rows;
 #pragma unroll
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
             mma_bf16(tm1, a1d, b1d, idesc, 0u);
             mma_commit(&mma_bar[g]);
         }
+        if (!RING && NSTG == 1 && c.valid) fetch_dense(c.tile, 0);      // the single staging buffer is free again (barrier above)
         const bool have_next = c.valid;
         const long long next_tile = c.tile;
         const int next_e = c.e, next_tp = c.tp;
@@ -335,15 +346,15 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
         mbar_wait(&mma_bar[g], mph);
         mph ^= 1u;
         tc_fence_after();
-        // ---- A2 = tanh(D1) as bf16
+        // ---- A2 = tanh(D1) as bf16, 16 accumulator columns at a time (register budget of 768 threads)
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            B2P_LD32(tm1 + tlane + 32 * half, v);
+        for (int qt = 0; qt < 4; ++qt) {
+            uint32_t v[16];
+            B2P_LD16(tm1 + tlane + 16 * qt, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            unsigned char *row = A2 + (gt >> 3) * SBO2 + (gt & 7) * 16 + (4 * half) * 128;
+            unsigned char *row = A2 + (gt >> 3) * SBO2 + (gt & 7) * 16 + (2 * qt) * 128;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -369,13 +380,13 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
         // ---- head: mean = tanh(D2) . w3 + b3
         float acc0 = b3, acc1 = 0.f;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            B2P_LD32(tm2 + tlane + 32 * half, v);
+        for (int qt = 0; qt < 4; ++qt) {
+            uint32_t v[16];
+            B2P_LD16(tm2 + tlane + 16 * qt, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 w = *reinterpret_cast<const float4 *>(w3s + 32 * half + 4 * c);
+            for (int c = 0; c < 4; ++c) {
+                const float4 w = *reinterpret_cast<const float4 *>(w3s + 16 * qt + 4 * c);
                 float t0, t1, t2, t3;
                 if (TANH == 2) {
                     const uint32_t p0 = tanh_bf16x2(pack_bf16x2(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1])));
