@@ -221,3 +221,39 @@ def test_env_and_policy_on_a_device_that_is_not_current():
     for a, b in zip(*results):
         for x, y in zip(a, b):
             assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+
+
+def test_outputs_stay_inside_their_buffers():
+    """Guard bands around caller-owned outputs (compute-sanitizer is not available on the GPU pool): the policy
+    kernel's action vector (dense and ring front ends, ragged row counts) and the observation matrix of the three
+    step paths (warp-per-env, resident-minibatch pipeline, tcgen05 pipeline) written through `obs_out`."""
+    pad = 1024
+    policy = make_policy(15, seed=6)
+    dev = DevicePolicy.from_torch(policy.pi)
+    for rows in (1, 127, 128, 129, 100003):
+        obs = torch.randn(rows, 15, device='cuda')
+        buf = torch.full((rows + 2 * pad,), float('nan'), device='cuda')
+        dev.act(obs, buf[pad:pad + rows])
+        assert torch.isnan(buf[:pad]).all() and torch.isnan(buf[pad + rows:]).all() and not torch.isnan(buf[pad:pad + rows]).any(), rows
+    rng = np.random.RandomState(0)
+    shapes = [(ProblemSpec('softmax', 4, (), 3), 150, 7), (ProblemSpec('softmax', 784, (), 10), 320, 5),
+              (ProblemSpec('softmax', 784, (64,), 10), 320, 3)]
+    for spec, rows, envs in shapes:
+        feats = rng.uniform(size=(rows, spec.num_features)).astype(np.float32)
+        labels = rng.randint(0, spec.num_outputs, rows).astype(np.int32)
+        env = BatchedOptEnv(spec, feats, labels, envs, batch_size=32, max_batches=3, perms=env_permutations(rows, list(range(envs))))
+        env.reset()
+        n = env.num_rows * env.obs_dim
+        buf = torch.full((n + 2 * pad,), float('nan'), device='cuda')
+        window = buf[pad:pad + n].view(env.num_rows, env.obs_dim)
+        gen = torch.Generator(device='cuda').manual_seed(1)
+        for t in range(4):                                     # the third step ends every episode: auto-reset rows too
+            env.step(torch.rand(env.num_rows, device='cuda', generator=gen) * 2, obs_out=window)
+            assert torch.isnan(buf[:pad]).all() and torch.isnan(buf[pad + n:]).all() and not torch.isnan(window).any(), (spec, t)
+        if spec.hidden:
+            act = torch.full((env.num_rows + 2 * pad,), float('nan'), device='cuda')
+            dev.act_env(env, act[pad:pad + env.num_rows])
+            assert torch.isnan(act[:pad]).all() and torch.isnan(act[pad + env.num_rows:]).all()
+            assert not torch.isnan(act[pad:pad + env.num_rows]).any()
+        env.close()
+    dev.close()
