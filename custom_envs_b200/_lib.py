@@ -28,7 +28,7 @@ EXPORTS = (
     'b2d_last_error', 'b2d_resize_nearest', 'b2d_minmax_workspace', 'b2d_column_minmax',
     'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot',
     # shared per-agent policy (include/b200policy.h)
-    'b2p_create', 'b2p_destroy', 'b2p_last_error', 'b2p_set_weights', 'b2p_act', 'b2p_act_env')
+    'b2p_create', 'b2p_destroy', 'b2p_last_error', 'b2p_set_weights', 'b2p_act', 'b2p_act_env', 'b2p_set_seed_counter')
 DTYPE_U8, DTYPE_I32, DTYPE_F32, DTYPE_F64 = range(4)
 
 
@@ -100,6 +100,7 @@ def load():
     lib.b2p_last_error.argtypes = [vp]
     lib.b2p_last_error.restype = ctypes.c_char_p
     lib.b2p_set_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.b2p_set_seed_counter.argtypes = [vp, vp]
     lib.b2p_act.argtypes = [vp, vp, i64, vp, f32, u64, f32, f32, vp]
     lib.b2p_act_env.argtypes = [vp, vp, vp, f32, u64, f32, f32, vp]
     if lib.b2e_abi_version() != 2:

@@ -62,6 +62,7 @@ struct Args {
     long long rows, tiles;
     int units, segs;                  // ring front end: units = envs x segments of an env's tiles
     unsigned long long seed;
+    const unsigned long long *seed_counter;   // added to seed when set (b2p_set_seed_counter)
     float noise_std, low, high;
     int obs_dim, bulk_ok;
 };
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
     const uint32_t tm1 = tmem + 64 * g, tm2 = tm1;
     const uint32_t tlane = (uint32_t)(wq * 32) << 16;
     const float b3 = w3s[HID];
+    const unsigned long long seed = a.seed + (a.seed_counter ? *a.seed_counter : 0ull);
 
     // ---- front ends
     const int tiles_per_env = RING ? (d.P + TILE - 1) / TILE : 1;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
             orow = tile * TILE + gt;
             live = orow < a.rows;
         }
-        if (a.noise_std != 0.f) mean = fmaf(a.noise_std, row_noise(a.seed, orow), mean);
+        if (a.noise_std != 0.f) mean = fmaf(a.noise_std, row_noise(seed, orow), mean);
         if (live) a.out[orow] = fminf(fmaxf(mean, a.low), a.high);
         have = have_next; tile = next_tile; cur_e = next_e; cur_tp = next_tp;
     }
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_kernel(const __grid_constan
 struct b2p_policy {
     int device, obs_dim, tanh_mode, num_sms;
     float *weights;                  // w1 [64, obs_dim] | b1 | w2 [64, 64] | b2 | w3 | b3
+    const unsigned long long *seed_counter;
     bool have_weights;
     std::string error;
 };
@@ -497,12 +500,19 @@ int b2p_create(int device, int obs_dim, int tanh_mode, b2p_handle *out) {
     if (!h) return pfail(nullptr, "b2p_create: out of host memory");
     h->device = device; h->obs_dim = obs_dim; h->tanh_mode = tanh_mode; h->num_sms = prop.multiProcessorCount;
     h->have_weights = false;
+    h->seed_counter = nullptr;
     const size_t count = (size_t)pol::HID * obs_dim + pol::HID + pol::HID * pol::HID + pol::HID + pol::HID + 1;
     if (cudaMalloc((void **)&h->weights, count * sizeof(float)) != cudaSuccess) {
         delete h;
         return pfail(nullptr, "b2p_create: cudaMalloc failed");
     }
     *out = h;
+    return 0;
+}
+
+int b2p_set_seed_counter(b2p_handle h, const uint64_t *counter) {
+    if (!h) return 1;
+    h->seed_counter = reinterpret_cast<const unsigned long long *>(counter);
     return 0;
 }
 
@@ -543,6 +553,7 @@ int b2p_act(b2p_handle h, const float *obs, int64_t rows, float *actions_out, fl
     memset(&a, 0, sizeof(a));
     fill_weights(h, a);
     a.obs = obs; a.out = actions_out; a.rows = rows; a.tiles = (rows + pol::TILE - 1) / pol::TILE;
+    a.seed_counter = h->seed_counter;
     a.seed = seed; a.noise_std = noise_std; a.low = low; a.high = high;
     a.bulk_ok = (reinterpret_cast<uintptr_t>(obs) & 15u) == 0 ? 1 : 0;
     Dev d;
@@ -578,6 +589,7 @@ int b2p_act_env(b2p_handle h, b2e_handle env, float *actions_out, float noise_st
     segs = segs > max_segs ? max_segs : segs;
     a.segs = segs < 1 ? 1 : segs;
     a.units = dv->E * a.segs;
+    a.seed_counter = h->seed_counter;
     a.seed = seed; a.noise_std = noise_std; a.low = low; a.high = high;
     const int grid = a.units < h->num_sms ? a.units : h->num_sms;
     const cudaError_t err = dv->H == 5 ? launch_policy<1>(h->tanh_mode, grid, (cudaStream_t)stream, a, *dv)

@@ -33,6 +33,7 @@ class DevicePolicy:
         self.low, self.high = float(low), float(high)
         self.noise_std = 0.0 if log_std is None else float(torch.as_tensor(log_std).exp())
         self.calls = 0
+        self.seed_counter = None
         handle = ctypes.c_void_p()
         if self.lib.b2p_create(self.device.index or 0, self.obs_dim, int(tanh_mode), ctypes.byref(handle)):
             raise _lib.B200EnvError(self.lib.b2p_last_error(None).decode())
@@ -68,6 +69,16 @@ class DevicePolicy:
         assert tensors[0].shape == (64, self.obs_dim) and tensors[2].shape == (64, 64) and tensors[4].numel() == 64
         self._check(self.lib.b2p_set_weights(self.handle, *[_ptr(t) for t in tensors], self._stream()))
         torch.cuda.current_stream(self.device).synchronize()      # the sources may be temporaries
+
+    def use_seed_counter(self, enabled=True):
+        """Draw the noise seed from a device counter (``self.seed_counter``, int64 [1]) added to the seed argument:
+        launches captured in a CUDA graph then see fresh noise on every replay if the graph also advances it."""
+        if enabled and self.seed_counter is None:
+            self.seed_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ptr = ctypes.c_void_p(self.seed_counter.data_ptr() if enabled else 0)
+        self._check(self.lib.b2p_set_seed_counter(self.handle, ptr))
+        if not enabled:
+            self.seed_counter = None
 
     def _seed(self, seed):
         self.calls += 1
@@ -119,22 +130,53 @@ def reference_actions(tower, obs, low=-4.0, high=6.0, bf16=True):
 
 
 @torch.no_grad()
-def device_policy_rollout(env, policy, steps, ring_only=True, on_step=None):
+def device_policy_rollout(env, policy, steps, ring_only=True, on_step=None, use_graph=False):
     """``steps`` lock-step env steps driven by a ``DevicePolicy``; with ``ring_only`` the env never
     writes observation rows and the policy reads the rings (nothing but E rewards / flags / info rows
-    and the action vector exists per step).  Returns (per-env reward sums [E], finished episodes)."""
+    and the action vector exists per step).  Returns (per-env reward sums [E], finished episodes).
+
+    ``use_graph``: capture policy -> step -> bookkeeping for two steps (the pipeline's gradient buffers
+    alternate) into one CUDA graph and replay it: no per-step Python or launch gaps.  Needs an even
+    ``steps``, ``ring_only`` and no ``on_step``; the policy's noise seed then advances on the device."""
     actions = torch.empty(env.num_rows, dtype=torch.float32, device=env.device)
     returns = torch.zeros(env.num_envs, dtype=torch.float64, device=env.device)
     finished = torch.zeros((), dtype=torch.int64, device=env.device)
     obs = env.obs
-    for t in range(steps):
+
+    def one_step():
         if ring_only:
-            policy.act_env(env, actions)
+            policy.act_env(env, actions, seed=0 if use_graph else None)
         else:
-            policy.act(obs, actions)
-        obs, reward, done, info = env.step(actions, ring_only=ring_only)
-        returns += reward
-        finished += done.sum()
+            policy.act(obs, actions, seed=0 if use_graph else None)
+        out = env.step(actions, ring_only=ring_only)
+        returns.add_(out[1])
+        finished.add_(out[2].sum())
+        return out
+
+    if use_graph:
+        if steps % 2 or not ring_only or on_step is not None:
+            raise ValueError('use_graph needs an even number of ring-only steps and no on_step hook')
+        policy.use_seed_counter(True)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side):                      # steps 1 and 2 eagerly (lazy module loading outside the capture)
+            for _ in range(2):
+                one_step()
+                policy.seed_counter.add_(1)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+        torch.cuda.synchronize(env.device)
+        with torch.cuda.graph(graph):
+            for _ in range(2):
+                one_step()
+                policy.seed_counter.add_(1)
+        for _ in range(steps // 2 - 1):
+            graph.replay()
+        torch.cuda.synchronize(env.device)
+        policy.use_seed_counter(False)
+        return returns, int(finished.item())
+    for t in range(steps):
+        obs, reward, done, info = one_step()
         if on_step is not None:
             on_step(t, obs, reward, done, info)
     return returns, int(finished.item())

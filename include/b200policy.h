@@ -54,6 +54,11 @@ const char *b2p_last_error(b2p_handle h);
 int b2p_set_weights(b2p_handle h, const float *w1, const float *b1, const float *w2,
                     const float *b2, const float *w3, const float *b3, void *stream);
 
+/* Optional: a device counter added to `seed` by every later b2p_act / b2p_act_env launch (NULL = none).  The caller
+ * advances it on the stream between launches; a CUDA graph that captured the launches then draws fresh noise on
+ * every replay although the seed argument is baked into the graph. */
+int b2p_set_seed_counter(b2p_handle h, const uint64_t *counter);
+
 /* obs float32 [rows, obs_dim] dense -> actions_out float32 [rows].  noise_std = exp(log_std) of the
  * diagonal Gaussian (0 = deterministic, `model.predict(deterministic=True)`); the noise of a row is a
  * counter-based hash of (seed, row). */

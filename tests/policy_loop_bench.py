@@ -69,6 +69,11 @@ for mode, tag in ((0, 'tanh.approx.f32'), (1, 'layer 1 tanh.approx.bf16x2'), (2,
     ms, (_, finished) = timed(lambda: device_policy_rollout(env, dev, steps, ring_only=True), 1)
     ms /= steps
     print('  rollout on the rings (ring-only env steps): %.2f ms/step, %.0f env-steps/s' % (ms, envs / ms * 1e3), flush=True)
+    if mode == 0:
+        ms, (_, finished) = timed(lambda: device_policy_rollout(env, dev, steps + 2, ring_only=True, use_graph=True), 1)
+        ms /= steps + 2
+        print('  the same as a CUDA graph of two steps (capture included in the timing): %.2f ms/step, %.0f env-steps/s'
+              % (ms, envs / ms * 1e3), flush=True)
     dev.close()
 # the ring-only env step alone
 gen_actions = torch.rand(env.num_rows, device=env.device) * 3

@@ -257,3 +257,37 @@ def test_outputs_stay_inside_their_buffers():
             assert not torch.isnan(act[pad:pad + env.num_rows]).any()
         env.close()
     dev.close()
+
+
+def test_graph_captured_rollout_equals_the_eager_rollout():
+    """policy -> ring-only step -> bookkeeping captured as one CUDA graph of two steps and replayed: the same returns,
+    episode count and parameters as the eager loop (deterministic policy); with exploration noise the device seed
+    counter makes every replay draw fresh noise (the actions of consecutive steps differ)."""
+    policy = make_policy(15, seed=2, scale=1.5)
+    results = []
+    for use_graph in (False, True):
+        env = small_env(num_envs=4, max_batches=5, materialize_obs=False)
+        dev = DevicePolicy.from_torch(policy.pi)
+        returns, finished = device_policy_rollout(env, dev, 8, ring_only=True, use_graph=use_graph)
+        results.append((returns.cpu().numpy(), finished, env.get_state('params').cpu().numpy()))
+        dev.close()
+        env.close()
+    assert results[0][1] == results[1][1] == 4
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][2], results[1][2])
+    # noise: replays of the same graph must not repeat the draw
+    env = small_env(num_envs=2, max_batches=50, materialize_obs=False)
+    dev = DevicePolicy.from_torch(policy.pi, log_std=torch.tensor(-1.0))
+    dev.use_seed_counter(True)
+    actions = torch.empty(env.num_rows, device='cuda')
+    graph = torch.cuda.CUDAGraph()
+    dev.act_env(env, actions, seed=0)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph):
+        dev.act_env(env, actions, seed=0)
+        dev.seed_counter.add_(1)
+    graph.replay()
+    first = actions.clone()
+    graph.replay()
+    assert not torch.equal(first, actions) and int(dev.seed_counter.item()) == 2
+    dev.close()
+    env.close()
