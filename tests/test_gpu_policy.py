@@ -80,14 +80,14 @@ def test_gaussian_noise_is_per_row_and_reproducible():
     assert abs(torch.corrcoef(torch.stack([z[:-1], z[1:]]))[0, 1].item()) < 0.01
 
 
-def small_env(num_envs=3, max_batches=6, row_order='lexicographic', materialize_obs=True, seed=0):
+def small_env(num_envs=3, max_batches=6, row_order='lexicographic', materialize_obs=True, seed=0, max_history=5):
     """The BASELINE config-4 problem shape (MLP 784-64-10: the tcgen05 pipeline) on a small data set."""
     rng = np.random.RandomState(seed)
     rows = 320
     feats = rng.uniform(size=(rows, 784)).astype(np.float32)
     labels = rng.randint(0, 10, rows).astype(np.int32)
     env = BatchedOptEnv(ProblemSpec('softmax', 784, (64,), 10), feats, labels, num_envs, batch_size=32,
-                        max_batches=max_batches, max_history=5, row_order=row_order,
+                        max_batches=max_batches, max_history=max_history, row_order=row_order,
                         perms=env_permutations(rows, list(range(num_envs))), init_seed=9,
                         materialize_obs=materialize_obs)
     env.reset()
@@ -104,11 +104,12 @@ def check_info(got, want, msg):
     np.testing.assert_allclose(got[:, SUMMED_TWICE], want[:, SUMMED_TWICE], rtol=2e-6, atol=0, err_msg=msg)
 
 
-@pytest.mark.parametrize('row_order', ['lexicographic', 'natural'])
-def test_ring_front_end_equals_dense_front_end(row_order):
+@pytest.mark.parametrize('row_order,depth', [('lexicographic', 5), ('natural', 5), ('lexicographic', 3), ('natural', 1)])
+def test_ring_front_end_equals_dense_front_end(row_order, depth):
     """act_env reads the rings, act reads the observation rows the same step wrote: identical actions,
     from the reset observation (all -1), through a filling history, to a full one."""
-    env = small_env(row_order=row_order)
+    env = small_env(row_order=row_order, max_history=depth)          # depth != 5: the run-time-depth ring front end
+    assert env.obs_dim == 3 * depth
     policy = make_policy(env.obs_dim, seed=1, scale=1.5)
     dev = DevicePolicy.from_torch(policy.pi)
     gen = torch.Generator(device='cuda').manual_seed(0)
