@@ -80,13 +80,16 @@ def test_gaussian_noise_is_per_row_and_reproducible():
     assert abs(torch.corrcoef(torch.stack([z[:-1], z[1:]]))[0, 1].item()) < 0.01
 
 
-def small_env(num_envs=3, max_batches=6, row_order='lexicographic', materialize_obs=True, seed=0, max_history=5):
-    """The BASELINE config-4 problem shape (MLP 784-64-10: the tcgen05 pipeline) on a small data set."""
+def small_env(num_envs=3, max_batches=6, row_order='lexicographic', materialize_obs=True, seed=0, max_history=5,
+              hidden=(64,)):
+    """The BASELINE config-4 problem shape (MLP 784-64-10: the tcgen05 pipeline) on a small data set; other
+    ``hidden`` tuples select the other large-problem pipelines (() = config 3's resident-minibatch eval kernel,
+    two layers = the generic dense stack)."""
     rng = np.random.RandomState(seed)
     rows = 320
     feats = rng.uniform(size=(rows, 784)).astype(np.float32)
     labels = rng.randint(0, 10, rows).astype(np.int32)
-    env = BatchedOptEnv(ProblemSpec('softmax', 784, (64,), 10), feats, labels, num_envs, batch_size=32,
+    env = BatchedOptEnv(ProblemSpec('softmax', 784, tuple(hidden), 10), feats, labels, num_envs, batch_size=32,
                         max_batches=max_batches, max_history=max_history, row_order=row_order,
                         perms=env_permutations(rows, list(range(num_envs))), init_seed=9,
                         materialize_obs=materialize_obs)
@@ -101,7 +104,12 @@ def check_info(got, want, msg):
     got, want = got.cpu().numpy(), want.cpu().numpy()
     rest = [c for c in range(got.shape[1]) if c not in SUMMED_TWICE]
     np.testing.assert_array_equal(got[:, rest], want[:, rest], err_msg=msg)
-    np.testing.assert_allclose(got[:, SUMMED_TWICE], want[:, SUMMED_TWICE], rtol=2e-6, atol=0, err_msg=msg)
+    a, b = got[:, SUMMED_TWICE], want[:, SUMMED_TWICE]
+    # sums holding a nan_to_num(x/0) = FLT_MAX term (zero-initialised biases) overflow in one grouping of the fp32
+    # partial sums and not in the other: outside the parity domain; both sides must agree that they are huge
+    huge = ~(np.isfinite(a) & (np.abs(a) < 1e30)) | ~(np.isfinite(b) & (np.abs(b) < 1e30))
+    assert np.all((np.abs(a[huge]) > 1e30) & (np.abs(b[huge]) > 1e30)), msg
+    np.testing.assert_allclose(a[~huge], b[~huge], rtol=2e-6, atol=0, err_msg=msg)
 
 
 @pytest.mark.parametrize('row_order,depth', [('lexicographic', 5), ('natural', 5), ('lexicographic', 3), ('natural', 1)])
@@ -124,13 +132,14 @@ def test_ring_front_end_equals_dense_front_end(row_order, depth):
     env.close()
 
 
-def test_ring_only_step_is_the_same_env_step():
+@pytest.mark.parametrize('hidden', [(64,), (), (24, 8)], ids=['tcgen05', 'resident-minibatch', 'generic-stack'])
+def test_ring_only_step_is_the_same_env_step(hidden):
     """Two identical env batches, one stepping with observation rows, one ring-only (one of them without
     an observation matrix at all): parameters, rings, rewards, done flags and all 16 info columns agree
     step by step, across an episode end (the four statistics that the two paths sum in different fp32
     groupings -- states_mean / states_sum rebuilt from per-slot sums, adjusted_grad, grad_diff -- to 2e-6
     relative); a dense step afterwards returns identical observation rows."""
-    dense, ring = small_env(), small_env(materialize_obs=False)
+    dense, ring = small_env(hidden=hidden), small_env(materialize_obs=False, hidden=hidden)
     assert ring.obs is None
     gen = torch.Generator(device='cuda').manual_seed(4)
     for t in range(9):
