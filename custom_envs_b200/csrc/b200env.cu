@@ -3395,6 +3395,7 @@ struct b2e_env {
     bool eval_bulk;                  // ... and its bulk-copy / mbarrier pipelined form (B2E_EVAL_BULK=0 disables)
     int nchunks, eval_ctas_per_sm;   // B2E_CHUNKS experiment
     bool use_thin;                   // softmax regression: thin_eval_kernel
+    bool thin_fused;                 // ... whose cluster form runs eval / update / eval of a MultiOptLRs step as ONE launch (opt-in: B2E_THIN_FUSE=1)
     bool use_thin2;                  // ... its shared-memory-resident successor for 10 classes (b200thin.cu; B2E_THIN2=0 disables)
     size_t smem_thin;
     int thin_kc;
@@ -3841,7 +3842,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->X = h->targets_f = nullptr; h->labels = h->ord = h->perm = h->row_of_param = h->param_of_row = nullptr;
     h->w2 = h->g2 = h->ws = nullptr;
     h->use_tc2 = false; h->tc2 = nullptr; h->tc2_check = false;
-    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false; h->use_tiny = false; h->use_thin2 = false;
+    h->w = h->gprev = h->gnext = h->ringw = h->ringg = nullptr; h->sc = nullptr; h->part = nullptr; h->part_u = nullptr; h->part_r = nullptr; h->slot_abs = nullptr; h->reset_list = h->reset_count = nullptr; h->reset_loss = nullptr; h->reset_pipeline = false; h->use_tiny = false; h->use_thin2 = false; h->thin_fused = false;
     h->side = h->hi = nullptr; h->ev_fork = h->ev_join = nullptr;
     for (auto &ev : h->ev_chunk) ev = nullptr;
     auto bail = [&](const std::string &msg) { g_create_error = msg; b2e_destroy(h); return 1; };
@@ -4071,6 +4072,7 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     h->use_tiny = b2e_tiny_supported(&h->d) && !(getenv("B2E_TINY") && atoi(getenv("B2E_TINY")) == 0);
     h->use_thin2 = h->use_thin && b2e_thin2_supported(&h->d) && !(getenv("B2E_THIN2") && atoi(getenv("B2E_THIN2")) == 0) &&
                    b2e_thin2_prepare(&h->d) == 0;
+    h->thin_fused = h->use_thin2 && b2e_thin2_fused_step(&h->d);
     init_scalars_kernel<<<(d.E + 127) / 128, 128>>>(d);
     if (cudaDeviceSynchronize() != cudaSuccess) return bail("b2e_create: device initialisation failed");
     *out = h;
@@ -4273,7 +4275,7 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
         else if (h->eval_c) eval_kernel<false, 64, 112><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
         else eval_kernel<false><<<grid_ev, 256, h->smem_eval, main_s>>>(dv, a);
     } else if (h->use_thin) {
-        if (h->use_thin2) { if (b2e_thin2_launch(&d, &a, 0, h->num_sms, main_s)) return fail(h, "thin2 launch failed"); }
+        if (h->use_thin2) { if (b2e_thin2_launch(&d, &a, h->thin_fused ? 2 : 0, h->num_sms, main_s)) return fail(h, "thin2 launch failed"); }
         else { Dev dt = d; dt.KT = h->thin_kc;
           if (d.C == 10) thin_eval_kernel<false, 10><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a);
           else thin_eval_kernel<false><<<grid_ev, 256, h->smem_thin, main_s>>>(dt, a); }
@@ -4285,9 +4287,12 @@ int b2e_step(b2e_handle h, const float *actions, const int32_t *batch_idx,
     }
     mark(1);
     if (h->fuse_update && h->eval_bulk && h->use_eval_kernel && !h->use_tc) h->launches--;   // the first eval did it
+    else if (h->thin_fused) h->launches--;                   // thin3_eval_kernel<2> did update and second eval as well
     else update_kernel<<<dim3(d.nsegU, d.E), 256, 0, main_s>>>(d, a);
     mark(2);
-    if (h->use_tc2) {
+    if (h->thin_fused) {
+        h->launches--;
+    } else if (h->use_tc2) {
         if (b2e_tc2_launch(h->tc2, &d, &a, 1, main_s)) return fail(h, "tc2 launch failed");
     } else if (h->use_tc) {
         tc_eval_kernel<true><<<grid_ev, 256, h->smem_tc, main_s>>>(dv, a);

@@ -995,3 +995,45 @@ def test_resident_minibatch_eval_kernel_against_the_chunked_one(monkeypatch):
         np.testing.assert_allclose(new[4][:, 0], old[4][:, 0], rtol=RTOL, err_msg=str(t))
         np.testing.assert_allclose(new[0], old[0], rtol=20 * RTOL, atol=20 * RTOL, err_msg=str(t))
     assert ragged >= 2 * num_envs
+
+
+def test_one_launch_step_of_config_3_equals_the_three_launch_pipeline(monkeypatch):
+    """BASELINE config 3: `thin3_eval_kernel<2>` runs eval(w_{t-1}) -> update -> eval(w_t) -> scalars of a
+    MultiOptLRs step in one launch (rows and W stay in the cluster's shared memory, g0 never reaches HBM, no
+    update_kernel; opt-in with B2E_THIN_FUSE=1: it is not faster); the default runs the same arithmetic as eval /
+    update_kernel / eval.  Parameters, gradients,
+    rings, observation rows, rewards and done flags agree bit for bit over two episodes with a ragged last minibatch;
+    the update statistics (weights_mean/sum, actions_mean/std) are summed in another grouping."""
+    BatchedOptEnv, _ = _mods()
+    spec = SPECS['softmax_784x10'][0]
+    num_rows, num_envs = 304, 9
+    feats, targs = make_data(spec, num_rows)
+    perms = np.stack([orc.env_permutation(num_rows, 90 + s) for s in range(num_envs)])
+    runs = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.setenv('B2E_THIN_FUSE', '1')
+        else:
+            monkeypatch.delenv('B2E_THIN_FUSE', raising=False)
+        env = BatchedOptEnv(product_spec(spec), feats, targs, num_envs, batch_size=32, max_batches=11, perms=perms, init_seed=3)
+        rec = [env.reset().cpu().numpy().copy()]
+        launches = env.launch_count
+        gen = torch.Generator(device='cuda').manual_seed(2)
+        for t in range(24):
+            obs, rew, done, info = env.step(torch.rand(env.num_rows, device='cuda', generator=gen) * 2.5)
+            rec.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy(), info.cpu().numpy().copy(),
+                        {n: env.get_state(n).cpu().numpy() for n in ('params', 'grad_prev', 'adj_weights', 'adj_grads', 'adj_losses',
+                                                                    'raw_losses', 'raw_gsums', 'step', 'cursor')}))
+        runs.append((rec, env.launch_count - launches))
+        env.close()
+    assert runs[1][1] - runs[0][1] >= 2 * 24                  # two launches fewer per step
+    (fused_rec, _), (plain_rec, _) = runs
+    assert np.array_equal(fused_rec[0], plain_rec[0])
+    for t, (new, old) in enumerate(zip(fused_rec[1:], plain_rec[1:])):
+        assert np.array_equal(new[0], old[0]) and np.array_equal(new[1], old[1]) and np.array_equal(new[2], old[2]), t
+        for key in new[4]:
+            assert np.array_equal(new[4][key], old[4][key]), (t, key)
+        stats = [2, 3, 4, 5]
+        rest = [c for c in range(16) if c not in stats]
+        assert np.array_equal(new[3][:, rest], old[3][:, rest], equal_nan=True), t
+        np.testing.assert_allclose(new[3][:, stats], old[3][:, stats], rtol=1e-6, atol=1e-9, err_msg=str(t))
