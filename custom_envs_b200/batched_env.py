@@ -128,6 +128,8 @@ class BatchedOptEnv:
         dev = self.device
         self.obs = (torch.empty((self.num_rows, self.obs_dim), dtype=torch.float32, device=dev)
                     if materialize_obs else None)
+        self._fixed_ptrs = None
+        self._device_index = dev.index if dev.index is not None else torch.cuda.current_device()
         self.reward = torch.zeros(self.num_envs, dtype=torch.float32, device=dev)
         self.done = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
         self.info = torch.zeros((self.num_envs, _lib.INFO_STRIDE), dtype=torch.float64, device=dev)
@@ -216,6 +218,18 @@ class BatchedOptEnv:
         the rows then cross PCIe straight from the observation kernel).  ``ring_only``: do not
         write observation rows at all (obs is None in the result): the adjusted-history rings are
         the observation, read in place by a device policy (MultiOptLRs, large problems)."""
+        if (batch_idx is None and obs_out is None and not ring_only and self.obs is not None
+                and actions.dtype == torch.float32 and actions.device == self.device
+                and actions.is_contiguous() and actions.numel() == self.num_rows):
+            # the usual call: nothing to convert or check, raw stream handle, pointers of the fixed buffers cached
+            # (the tiny problems are bound by this host path: 14 -> 9 us per call)
+            if self._fixed_ptrs is None:
+                self._fixed_ptrs = (self.reward.data_ptr(), self.done.data_ptr(), self.info.data_ptr())
+            fixed = self._fixed_ptrs
+            if self.lib.b2e_step(self.handle, actions.data_ptr(), None, None, self.obs.data_ptr(), fixed[0], fixed[1], fixed[2],
+                                 torch._C._cuda_getCurrentRawStream(self._device_index)):
+                self._check(1)
+            return self.obs, self.reward, self.done, self.info
         actions = actions.reshape(-1)
         if actions.dtype != torch.float32 or actions.device != self.device or not actions.is_contiguous():
             actions = actions.to(self.device, torch.float32).contiguous()
