@@ -275,7 +275,7 @@ def sampled_parity(env, feats, labels, actions, max_batches=MAX_BATCHES, depth=H
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec, env_permutations
+    from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec, env_permutations_device
     from custom_envs_b200.vectorize.optvecenv import DeviceOptVecEnv
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -306,7 +306,7 @@ def gpu_arm(args):
     else:
         first_env, envs, envs_all = rank * args.envs, args.envs, args.envs * world
     seeds = range(first_env, first_env + envs)
-    perms = env_permutations(ROWS, list(seeds))
+    perms = env_permutations_device(ROWS, list(seeds), device)   # numpy's RandomState(seed).shuffle, generated on the device
     env = BatchedOptEnv(ProblemSpec('softmax', D, (HID,), C), feats, labels, envs,
                         batch_size=BATCH, max_batches=MAX_BATCHES, max_history=HIST,
                         row_order=args.row_order, perms=perms, device=device,

@@ -26,7 +26,7 @@ EXPORTS = (
     'b2e_set_trace', 'b2e_get_trace', 'b2e_launch_count',
     # data front-end (include/b200data.h)
     'b2d_last_error', 'b2d_resize_nearest', 'b2d_minmax_workspace', 'b2d_column_minmax',
-    'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot',
+    'b2d_normalize', 'b2d_rank_workspace', 'b2d_label_ranks', 'b2d_onehot', 'b2d_shuffle_permutations',
     # shared per-agent policy (include/b200policy.h)
     'b2p_create', 'b2p_destroy', 'b2p_last_error', 'b2p_set_weights', 'b2p_act', 'b2p_act_env', 'b2p_set_seed_counter')
 DTYPE_U8, DTYPE_I32, DTYPE_F32, DTYPE_F64 = range(4)
@@ -93,6 +93,7 @@ def load():
     lib.b2d_rank_workspace.restype = usize
     lib.b2d_label_ranks.argtypes = [vp, i64, vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
     lib.b2d_onehot.argtypes = [vp, i64, i32, vp, i32, vp, vp]
+    lib.b2d_shuffle_permutations.argtypes = [vp, i32, i64, i32, vp, vp]
     f32, u64 = ctypes.c_float, ctypes.c_uint64
     lib.b2p_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp)]
     lib.b2p_destroy.argtypes = [vp]

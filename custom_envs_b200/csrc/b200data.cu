@@ -36,6 +36,69 @@ int sm_count() {
     return count;
 }
 
+// ------------------------------------------------------------------ MT19937 shuffle (numpy legacy RandomState)
+// One lane per generator; the 624-word state of the warp's 32 generators sits in shared memory word-interleaved
+// ([624][32]: lane l touches bank l only).  mt19937_gen / mt19937_next / random_interval / _shuffle_raw of
+// numpy/random/src/mt19937 and numpy/random/_common restated.
+constexpr int kMtN = 624, kMtM = 397;
+
+__device__ __forceinline__ void mt_twist(uint32_t* mt, int lane) {       // regenerate all 624 words
+    auto at = [&](int i) -> uint32_t& { return mt[i * 32 + lane]; };
+    int kk = 0;
+    for (; kk < kMtN - kMtM; ++kk) {
+        const uint32_t y = (at(kk) & 0x80000000u) | (at(kk + 1) & 0x7fffffffu);
+        at(kk) = at(kk + kMtM) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    for (; kk < kMtN - 1; ++kk) {
+        const uint32_t y = (at(kk) & 0x80000000u) | (at(kk + 1) & 0x7fffffffu);
+        at(kk) = at(kk + (kMtM - kMtN)) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    const uint32_t y = (at(kMtN - 1) & 0x80000000u) | (at(0) & 0x7fffffffu);
+    at(kMtN - 1) = at(kMtM - 1) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__global__ void __launch_bounds__(32) mt_shuffle_kernel(const uint32_t* __restrict__ gen, int mode, int64_t count, int n,
+                                                         int32_t* __restrict__ out) {
+    extern __shared__ uint32_t mt[];                                       // [624][32]
+    const int lane = threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = g < count;
+    int pos = kMtN;
+    if (live) {
+        if (mode == B2D_MT_SEEDS) {                                        // mt19937_seed
+            uint32_t seed = gen[g];
+            for (int i = 0; i < kMtN; ++i) {
+                mt[i * 32 + lane] = seed;
+                seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u;
+            }
+        } else {
+            const uint32_t* st = gen + g * (kMtN + 1);
+            for (int i = 0; i < kMtN; ++i) mt[i * 32 + lane] = st[i];
+            pos = (int)st[kMtN];
+        }
+        int32_t* x = out + g * n;
+        for (int i = 0; i < n; ++i) x[i] = i;
+        for (int i = n - 1; i >= 1; --i) {                                 // _shuffle_raw
+            uint32_t mask = (uint32_t)i;                                   // random_interval(i): smallest 2^k - 1 >= i
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            uint32_t j;
+            do {
+                if (pos >= kMtN) { mt_twist(mt, lane); pos = 0; }
+                uint32_t y = mt[pos * 32 + lane];
+                ++pos;
+                y ^= y >> 11;                                              // tempering
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= y >> 18;
+                j = y & mask;
+            } while (j > (uint32_t)i);
+            const int32_t t = x[i];
+            x[i] = x[j];
+            x[j] = t;
+        }
+    }
+}
+
 constexpr int kThreads = 256;
 constexpr int kMinmaxBlocksPerSm = 4;
 constexpr int kMaxLabel = 65536;
@@ -290,6 +353,25 @@ int b2d_resize_nearest(const void* images, int dtype, int64_t count, int src_h, 
     }
     const cudaError_t err = cudaGetLastError();
     return err == cudaSuccess ? B2D_OK : fail(B2D_ECUDA, "b2d_resize_nearest", err);
+}
+
+int b2d_shuffle_permutations(const uint32_t* gen, int mode, int64_t count, int n, int32_t* out, void* stream) {
+    if (count < 0 || n < 0 || (mode != B2D_MT_SEEDS && mode != B2D_MT_STATES))
+        return fail(B2D_EINVAL, "b2d_shuffle_permutations: bad count, length or mode");
+    if (count == 0 || n == 0) return B2D_OK;
+    if (!gen || !out) return fail(B2D_EINVAL, "b2d_shuffle_permutations: null pointer");
+    const size_t smem = size_t(kMtN) * 32 * sizeof(uint32_t);
+    static bool opted_in = false;
+    if (!opted_in) {
+        const cudaError_t err = cudaFuncSetAttribute(mt_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return fail(B2D_ECUDA, "b2d_shuffle_permutations: shared memory", err);
+        opted_in = true;
+    }
+    const int64_t blocks = (count + 31) / 32;
+    if (blocks > 0x7fffffff) return fail(B2D_EINVAL, "b2d_shuffle_permutations: too many generators");
+    mt_shuffle_kernel<<<(unsigned)blocks, 32, smem, static_cast<cudaStream_t>(stream)>>>(gen, mode, count, n, out);
+    const cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? B2D_OK : fail(B2D_ECUDA, "b2d_shuffle_permutations", err);
 }
 
 size_t b2d_minmax_workspace(int cols) {

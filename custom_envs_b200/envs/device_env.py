@@ -9,7 +9,7 @@ from collections import OrderedDict, namedtuple
 
 import numpy as np
 
-from custom_envs_b200.batched_env import BatchedOptEnv, env_permutations
+from custom_envs_b200.batched_env import BatchedOptEnv, env_permutations_device
 from custom_envs_b200.compat import spaces
 from custom_envs_b200.envs.baseenvironment import BaseMultiEnvironment
 
@@ -67,7 +67,7 @@ class DeviceEnvFront(BaseMultiEnvironment):
     def _standalone(self):
         if self._backend is None:
             feats, targs = self.model.device_arrays()
-            perms = None if feats is None else env_permutations(len(feats), [self.random_generator])
+            perms = None if feats is None else env_permutations_device(len(feats), [self.random_generator], self.device)
             self._backend = BatchedOptEnv(self.model.spec, feats, targs, 1, row_order='natural',
                                           auto_reset=False, perms=perms, device=self.device,
                                           **self.backend_kwargs())
@@ -143,7 +143,7 @@ def fuse_fronts(fronts, device=None):
     feats, targs = first.model.device_arrays()
     perms = None
     if feats is not None:
-        perms = env_permutations(len(feats), [front.random_generator for front in fronts])
+        perms = env_permutations_device(len(feats), [front.random_generator for front in fronts], device or first.device)
     backend = BatchedOptEnv(first.model.spec, feats, targs, len(fronts), row_order='lexicographic',
                             auto_reset=True, perms=perms, device=device or first.device,
                             **first.backend_kwargs())

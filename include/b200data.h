@@ -64,6 +64,18 @@ int b2d_label_ranks(const int32_t* labels, int64_t count, int32_t* ranks, int32_
 int b2d_onehot(const int32_t* ranks, int64_t count, int num_labels, void* out, int out_dtype,
                void* workspace, void* stream);
 
+/* The permutation `np.random.RandomState(seed).shuffle(np.arange(n))` yields -- what every epoch-end / reset shuffle
+ * of one env applies to its data set (utils/utils_math.py:10-22 hands each of them the same generator state;
+ * utils/utils_common.py:12-23; dataset/inmemorydataset.py:24-28) -- for `count` generators at once, bit for bit:
+ * MT19937 as numpy's legacy RandomState drives it (init_genrand seeding, tempered 32-bit draws, masked rejection
+ * sampling of random_interval, Fisher-Yates from the last element down).
+ *   mode B2D_MT_SEEDS : `gen` = uint32 [count] integer seeds (RandomState(seed), 0 <= seed < 2^32)
+ *   mode B2D_MT_STATES: `gen` = uint32 [count][625], the 624-word key then the position, i.e. RandomState.get_state()[1:3]
+ *                       (a generator seeded any other way, e.g. classic gym's hashed seeds)
+ * out: int32 [count][n] device.  One thread per generator (the shuffle is a dependent chain of n - 1 swaps). */
+enum { B2D_MT_SEEDS = 0, B2D_MT_STATES = 1 };
+int b2d_shuffle_permutations(const uint32_t* gen, int mode, int64_t count, int n, int32_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,7 +36,7 @@ int main(int argc, char **argv) {
     RESOLVE(b2e_set_trace); RESOLVE(b2e_get_trace); RESOLVE(b2e_launch_count);
     RESOLVE(b2d_last_error); RESOLVE(b2d_resize_nearest); RESOLVE(b2d_minmax_workspace);
     RESOLVE(b2d_column_minmax); RESOLVE(b2d_normalize); RESOLVE(b2d_rank_workspace);
-    RESOLVE(b2d_label_ranks); RESOLVE(b2d_onehot);
+    RESOLVE(b2d_label_ranks); RESOLVE(b2d_onehot); RESOLVE(b2d_shuffle_permutations);
     RESOLVE(b2p_create); RESOLVE(b2p_destroy); RESOLVE(b2p_last_error); RESOLVE(b2p_set_weights);
     RESOLVE(b2p_act); RESOLVE(b2p_act_env); RESOLVE(b2p_set_seed_counter);
     *(void **)&abi_version = dlsym(lib, "b2e_abi_version");

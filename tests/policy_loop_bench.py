@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench                                                     # noqa: E402
-from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec, env_permutations   # noqa: E402
+from custom_envs_b200.batched_env import BatchedOptEnv, ProblemSpec, env_permutations_device   # noqa: E402
 from custom_envs_b200.vectorize.device_policy import DevicePolicy, device_policy_rollout   # noqa: E402
 from custom_envs_b200.vectorize.device_rollout import SharedMlpPolicy, device_rollout   # noqa: E402
 
@@ -18,7 +18,7 @@ envs = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 with_torch = (sys.argv[3] if len(sys.argv) > 3 else 'torch') == 'torch'
 feats, labels = bench.synthetic_data()
-perms = env_permutations(bench.ROWS, list(range(envs)))
+perms = env_permutations_device(bench.ROWS, list(range(envs)), 'cuda:0')
 
 
 def make_env(materialize_obs=True):

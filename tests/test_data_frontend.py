@@ -191,3 +191,29 @@ def test_load_data_on_device_equals_host_preparation():
         outs.append((np.stack([state[key] for key in sorted(state)]), reward, info['batch_loss']))
         env.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
+
+
+@pytest.mark.gpu
+def test_device_shuffle_is_numpys_randomstate_shuffle_bit_for_bit():
+    """the per-env epoch permutation, `np.random.RandomState(seed).shuffle(np.arange(N))`
+    (utils/utils_common.py:12-23 under utils/utils_math.py:10-22), generated on the device: MT19937 seeding, tempering,
+    the masked rejection sampling of `random_interval` and the Fisher-Yates order restated.  Integer seeds, generators
+    in an arbitrary state (classic gym's hash-seeded RandomState, a generator that has already been drawn from), the
+    sizes of the BASELINE data sets, tiny and degenerate lengths, more generators than one warp."""
+    import torch
+    from custom_envs_b200.batched_env import env_permutations, env_permutations_device
+    from custom_envs_b200.compat import gym_standin
+    for num_rows, seeds in [(150, list(range(70))), (60000, [0, 1, 2, 12345, 2 ** 32 - 1]), (1, [3]), (2, [4, 5]),
+                            (623, [7]), (625, [8]), (4097, list(range(1000, 1040)))]:
+        want = env_permutations(num_rows, seeds)
+        got = env_permutations_device(num_rows, seeds, 'cuda:0').cpu().numpy()
+        assert np.array_equal(got, want), (num_rows, seeds[:3])
+    # generators in arbitrary states: gym's np_random(seed) (init_by_array of a hashed seed), and one that was used before
+    gens = [gym_standin.np_random(s)[0] for s in range(5)]
+    used = np.random.RandomState(99)
+    used.uniform(size=1000)                                   # position inside the 624-word block
+    gens.append(used)
+    want = env_permutations(3000, gens)                       # copies the state, like use_random_state
+    got = env_permutations_device(3000, gens, 'cuda:0').cpu().numpy()
+    assert np.array_equal(got, want)
+    assert np.array_equal(env_permutations(3000, gens), want)  # ... and leaves the generators where they were
