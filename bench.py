@@ -472,7 +472,7 @@ def gpu_arm(args):
         step_gbs = BYTES_PER_ENV_STEP * envs / (launch_ms * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         threads = min(cores, 32)
-        cpu_steps = 30                          # ~12 s of host work on the pool's 16-32 core boxes
+        cpu_steps = args.cpu_steps              # 30: ~12 s of host work on the pool's 16-32 core boxes
         cpu_value, cpu_elapsed = cpu_env_steps_per_s(8, threads, cpu_steps, 1)
         faithful = cpu_faithful() if not args.skip_faithful else None
         line = {
@@ -542,6 +542,7 @@ def main():
                         help='strong scaling: this many envs sharded over all ranks (overrides --envs)')
     parser.add_argument('--skip-policy-loop', action='store_true', help='skip the device policy-in-the-loop figure')
     parser.add_argument('--skip-faithful', action='store_true', help='skip the ~25 s per-env-object CPU baseline')
+    parser.add_argument('--cpu-steps', type=int, default=30, help='steps of the vectorised CPU baseline sample (~12 s at 30)')
     args = parser.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

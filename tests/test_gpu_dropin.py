@@ -546,3 +546,37 @@ def test_script_call_sites_of_survey_8b(tmp_path):
         steps += 1
     assert steps == 4 and np.all(observations == -1)          # the auto-reset observation (concurrentvecenv.py:32-38)
     vec_env.close()
+
+
+def test_bench_line_carries_the_contract(tmp_path):
+    """`python bench.py` at a reduced env count: stdout is ONE JSON line with the keys the driver and the judge read
+    (metric, value, roofline against the measured peak, cpu_baseline, e2e with its copy volumes, gpu_launches, clocks),
+    the sampled oracle parity of the same run and the device policy loop."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--envs', '96', '--steps', '6', '--warmup', '3',
+                          '--e2e-steps', '2', '--skip-faithful', '--cpu-steps', '2'],
+                         capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline',
+                'parity', 'policy_loop'):
+        assert key in line, key
+    assert line['metric'] == 'env-steps/sec' and line['n_gpus'] == 1 and line['steps'] == 6 and line['dtype'] == 'f32'
+    assert line['higher_is_better'] is True and line['vs_baseline'] is None and line['data'] == 'synthetic'
+    assert abs(line['value'] - 96 * 1e3 / line['ms_per_step']) < 1e-6 * line['value']
+    roof = line['roofline']
+    assert roof['bound'] == 'hbm' and roof['unit'] == 'GB/s' and abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-9
+    assert {k['name'] for k in roof['kernels']} == {'eval_kernel<w_prev>', 'update_kernel', 'eval_kernel<w_new>', 'obs_kernel'}
+    e2e = line['e2e']
+    assert e2e['h2d_bytes_per_step'] == 96 * 50890 * 4 and e2e['d2h_bytes_per_step'] > 96 * 50890 * 15 * 4 and e2e['value'] > 0
+    assert line['gpu_launches'] >= 5 * 6
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] > 0
+    assert line['parity']['ok'] is True and line['parity']['done_equal'] is True
+    assert line['policy_loop']['value'] > 0 and 'error' not in line['policy_loop']
+    assert line['config']['episode_end_in_window']['envs_done'] == 96
