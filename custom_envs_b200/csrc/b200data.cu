@@ -361,11 +361,9 @@ int b2d_shuffle_permutations(const uint32_t* gen, int mode, int64_t count, int n
     if (count == 0 || n == 0) return B2D_OK;
     if (!gen || !out) return fail(B2D_EINVAL, "b2d_shuffle_permutations: null pointer");
     const size_t smem = size_t(kMtN) * 32 * sizeof(uint32_t);
-    static bool opted_in = false;
-    if (!opted_in) {
+    {   // the opt-in is per device: set it on every call (microseconds against a kernel of milliseconds)
         const cudaError_t err = cudaFuncSetAttribute(mt_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return fail(B2D_ECUDA, "b2d_shuffle_permutations: shared memory", err);
-        opted_in = true;
     }
     const int64_t blocks = (count + 31) / 32;
     if (blocks > 0x7fffffff) return fail(B2D_EINVAL, "b2d_shuffle_permutations: too many generators");
