@@ -1339,8 +1339,8 @@ __global__ void __launch_bounds__(O2_WARPS * 32) obs_kernel2(const __grid_consta
     float *rg_new = d.ringg + ((size_t)e * H + head) * d.Pp;
     float *obs_env = a.obs + (size_t)e * d.P * OD;
     const int nblk = (d.P + 31) >> 5;
-    const int u0 = chunk * O2_UNITS;
-    const int nu = min(O2_UNITS, nblk - u0);
+    const int u0 = chunk * d.obs_units;
+    const int nu = min(d.obs_units, nblk - u0);
     auto row_param = [&](int it) -> int {
         const int r = (u0 + it) * 32 + lane;
         return r < d.P ? (d.row_lex ? d.param_of_row[r] : r) : 0;
@@ -1463,8 +1463,8 @@ __global__ void __launch_bounds__(O2_WARPS * 32) obs_kernel3(const __grid_consta
     float *rg_new = d.ringg + ((size_t)e * H + head) * d.Pp;
     float *obs_env = a.obs + (size_t)e * d.P * OD;
     const int nblk = (d.P + 31) >> 5;
-    const int u0 = chunk * O2_UNITS;
-    const int nu = min(O2_UNITS, nblk - u0);
+    const int u0 = chunk * d.obs_units;
+    const int nu = min(d.obs_units, nblk - u0);
     float s_absadjg = 0.f, s_gdiff = 0.f, s_state = 0.f;
     int pn[R];
 #pragma unroll
@@ -3672,7 +3672,12 @@ int configure(b2e_handle h) {
             return fail(h, "B2E_OBS: rows per lane must be 1, 2 or 4");
         if (d.H != 5 || !d.split || c.env_kind != B2E_ENV_MULTIOPTLRS) h->obs_stages = h->obs_regs = 0;
         if (h->obs_stages || h->obs_regs) {
-            d.nseg = ((d.P + 31) / 32 + O2_UNITS - 1) / O2_UNITS;
+            // warp items of 32 units; small batches (BASELINE config 3: 8192 such items = 3.5 waves of the 296 resident
+            // CTAs) get 8-unit items, so that the last wave is 1/14 instead of 1/4 of the kernel
+            const int nblk = (d.P + 31) / 32;
+            const long long items32 = (long long)d.E * ((nblk + O2_UNITS - 1) / O2_UNITS);
+            d.obs_units = items32 < 8LL * 2 * O2_WARPS * h->num_sms ? 8 : O2_UNITS;
+            d.nseg = (nblk + d.obs_units - 1) / d.obs_units;
             const int npl1 = 2 * d.H + 2, stg = 32 * d.OD + 8;
             h->smem_obs2 = (size_t)O2_WARPS * (h->obs_stages * npl1 * 32 + (h->obs_bulk ? 2 : 1) * stg) * sizeof(float);
         }
@@ -3850,10 +3855,10 @@ int b2e_create(const b2e_config *cfg, b2e_handle *out) {
     if (cudaGetDeviceCount(&dev_count) != cudaSuccess || cfg->device < 0 || cfg->device >= dev_count)
         return bail("b2e_create: no such CUDA device");
     DeviceGuard guard(cfg->device);
-    if (configure(h)) return bail(h->error);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail("cudaGetDeviceProperties failed");
-    h->num_sms = prop.multiProcessorCount;
+    h->num_sms = prop.multiProcessorCount;                  // configure sizes the observation kernel's work items with it
+    if (configure(h)) return bail(h->error);
     if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
         return bail("b2e_create: problem does not fit the fused kernel's shared memory (" +
                     std::to_string(h->smem_bytes) + " bytes needed)");

@@ -54,6 +54,7 @@ struct Dev {
         off_y, off_lb, off_misc;
     int stage_stride, xslack;
     int split, nseg;
+    int obs_units;                   // 32-row units per warp item of the observation kernel (32; fewer for small batches: more waves)
     int fast, cg;                    // register-tiled GEMM path (N1 % 8 == 0, B <= 32, 256 threads)
     int ev_X0, ev_X1, ev_W0, ev_W1, ev_XS;   // eval kernel: streamed X / W tile buffers
     int nsegU;
